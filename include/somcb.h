@@ -1,0 +1,129 @@
+/*
+ * somcb.h -- C-ABI of libsomcb.so: the B200 (sm_100a) SOM-codebook hot path.
+ *
+ * The reference (Vinmwaura/Quantized-Autoregression-Image-Generator) is pure Python and has no
+ * FFI of its own; its boundary for this path is the class models/Codebook.py::Codebook.  Every
+ * entry point below names the reference lines it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on it (no host
+ *     synchronisation inside), so host scalars are passed by value, results stay on the device;
+ *   - the library never allocates, frees or retains device memory: inputs, outputs and
+ *     workspaces are caller-owned (size a workspace with the matching *_workspace_bytes call);
+ *   - return 0 on success, a negative SOM_E_* code for argument/shape/workspace errors, a
+ *     positive cudaError_t for a failed launch; som_last_error() gives the thread-local text;
+ *   - patch geometry (n_img, C, H, Wd, pH, pW) describes an fp32 contiguous NCHW batch that is
+ *     cut into (H/pH)*(Wd/pW) patches per image, patch s = ph*(Wd/pW)+pw, feature
+ *     d = c*pH*pW + i*pW + j  <->  x[n, c, ph*pH+i, pw*pW+j]   (models/layers.py:8-34).
+ *     A pre-flattened (n, D) row matrix is the geometry (n, 1, 1, D, 1, D).
+ */
+#ifndef SOMCB_H_
+#define SOMCB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SOM_API __attribute__((visibility("default")))
+#else
+#define SOM_API
+#endif
+
+/* error codes */
+#define SOM_OK               0
+#define SOM_E_BADARG        -1   /* null pointer, non-positive size, misaligned buffer          */
+#define SOM_E_SHAPE         -2   /* H % pH != 0, K too large for the variant, ...               */
+#define SOM_E_WORKSPACE     -3   /* workspace smaller than *_workspace_bytes says               */
+#define SOM_E_UNSUPPORTED   -4   /* variant not available for this shape / device               */
+
+/* BMU kernel variants (static rule in som_bmu_pick_variant; no runtime autotuner) */
+#define SOM_BMU_AUTO         0
+#define SOM_BMU_FFMA         1   /* fp32 FFMA register-tiled kernel, any shape                  */
+#define SOM_BMU_TC3X         2   /* tcgen05 kind::tf32, 3xTF32 error-compensated, TMEM argmin   */
+
+SOM_API int         som_version(void);
+SOM_API const char* som_last_error(void);
+/* SM count and compute capability of the current device (host pointers). */
+SOM_API int         som_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K0: per-weights-version precompute -------------------------------------------------
+ * c_norm2[j] = ||W[j]||^2 (fp32).  Replaces the [W, 1, ||W||^2] operand torch.cdist builds
+ * on every call (models/Codebook.py:86-88). */
+SOM_API int som_prepare_codebook_f32(const float* W, int K, int D, float* c_norm2, void* stream);
+
+/* ---- K1: Best-Matching-Unit search ------------------------------------------------------
+ * Replaces Codebook.get_patches_bmu (models/Codebook.py:77-99): patchify + torch.cdist +
+ * argmin, first index on ties.  The (N*Seq) x K distance matrix is never materialised.
+ *   out_idx[p]  = unit_offset + argmin_j ( ||W_j||^2 - 2 x_p . W_j )        (int64)
+ *   out_rd[p]   = that minimum "reduced distance" (= d^2 - ||x_p||^2), or NULL
+ * unit_offset / out_rd serve the unit-sharded mode (som_merge_candidates).              */
+SOM_API size_t som_bmu_workspace_bytes(int64_t n_patches, int D, int K, int variant);
+SOM_API int    som_bmu_pick_variant(int64_t n_patches, int D, int K);
+SOM_API int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                     const float* W, const float* c_norm2, int K, int64_t unit_offset,
+                     int64_t* out_idx, float* out_rd,
+                     void* ws, size_t ws_bytes, int variant, void* stream);
+
+/* ---- K1b: merge per-shard candidates (new; multi-GPU unit-sharded search) ---------------
+ * rd, idx are (R, n) row-major; picks the smaller rd, ties -> the smaller global index,
+ * which reproduces the single-device first-minimum rule when shards are index-ordered.   */
+SOM_API int som_merge_candidates(const float* rd, const int64_t* idx, int R, int64_t n,
+                         int64_t* out_idx, float* out_rd, void* stream);
+
+/* ---- K5: BMU hit histogram --------------------------------------------------------------
+ * counts[j] += #{p : idx[p] == j}.  Replaces the Python dict loop of
+ * prune_codebook.py:129-142.  Indices outside [0, K) are ignored.                        */
+SOM_API int som_histogram_i64(const int64_t* idx, int64_t n, int K, int64_t* counts, void* stream);
+
+/* ---- K3: Gaussian neighbourhood filter along the unit axis ------------------------------
+ * out = scale * T @ in,  T[a,j] = expf(-( float((j-a)^2) / float(two_var) )),
+ * two_var = 2 * -(neighbourhood_range / (2 ln 0.1))   (models/Codebook.py:112-130).
+ * T is exactly banded in fp32, so this is the dense S @ W of the reference after the
+ * factorisation S = onehot(bmu) @ T.  `in` and `out` are K x D, distinct. */
+SOM_API int som_filter_f32(const float* in, float* out, int K, int D, double neighbourhood_range,
+                   float scale, void* stream);
+
+/* ---- K2: per-unit accumulation (segmented by BMU, deterministic, no float atomics) ------
+ *   Wt != NULL:  Rbar[a] = sum_{p: bmu[p]==a} (Wt[a] - x_p),  sse = sum_p ||Wt[bmu_p]-x_p||^2
+ *   Wt == NULL:  Rbar[a] = sum_{p: bmu[p]==a} x_p             (autograd backward of the gather)
+ * Replaces the S^T @ grad half of autograd for models/Codebook.py:128-130 together with
+ * F.mse_loss (train_codebook.py:233-240).  Rbar (K x D) is fully overwritten.  counts (K,
+ * int64) and sse (1, double) may be NULL; both are overwritten, not accumulated.         */
+SOM_API size_t som_accumulate_workspace_bytes(int64_t n_patches, int D, int K);
+SOM_API int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                            const int64_t* bmu, const float* Wt, int K,
+                            float* Rbar, int64_t* counts, double* sse,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* ---- quantise: gather rows by BMU, fused unpatchify -------------------------------------
+ * out[n, c, ph*pH+i, pw*pW+j] = table[idx[n*Seq+s]][d].  With table = T@W this is the
+ * Gaussian branch of get_quantized_patches + unpatchify (models/Codebook.py:128-134,
+ * 156-164); with table = W it is the hard branch (:132) and get_quantized_image
+ * (:138-154).  Indices must be in [0, K).                                                */
+SOM_API int som_quantize_nchw_f32(const int64_t* idx, const float* table, int K,
+                          int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                          float* out, void* stream);
+
+/* ---- K4: Adam on the codebook (fast-path trainer; the drop-in leaves it to torch) -------
+ * torch.optim.Adam(betas=(b1,b2), eps) single-tensor rule, no weight decay / amsgrad
+ * (train_codebook.py:183-186, 242).  `step` is the 1-based step count after increment.   */
+SOM_API int som_adam_f32(float* W, float* m, float* v, const float* g, int64_t n,
+                 double lr, double b1, double b2, double eps, int64_t step, void* stream);
+
+/* ---- row compaction for pruning ----------------------------------------------------------
+ * out[r] = W[keep[r]] for r < n_keep (prune_codebook.py:161-162).                        */
+SOM_API int som_gather_rows_f32(const float* W, int D, const int64_t* keep, int64_t n_keep,
+                        float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOMCB_H_ */

@@ -1,0 +1,364 @@
+// K2: per-unit accumulation, segmented by BMU.
+//
+//   Wt != NULL:  Rbar[a] = sum_{p: bmu[p]==a} (Wt[a] - x_p)     sse = sum_p ||Wt[bmu_p] - x_p||^2
+//   Wt == NULL:  Rbar[a] = sum_{p: bmu[p]==a} x_p
+//
+// Together with the neighbourhood filter this is the S^T @ grad half of the reference's autograd
+// step for models/Codebook.py:128-130 + F.mse_loss (train_codebook.py:233-240), after the exact
+// factorisation S = onehot(bmu) @ T.
+//
+// Pipeline (all on the caller's stream, fully deterministic, no floating-point atomics):
+//   1. keys = (int32) bmu, vals = patch id                          [pairs_kernel]
+//   2. stable LSD radix sort of (key, val) pairs over ceil(log2 K) bits   [cub::DeviceRadixSort:
+//      toolkit plumbing, ~1% of the step; order inside a segment is ascending patch id]
+//   3. offsets[a] = first sorted position with key >= a             [offsets_kernel]
+//   4. level 1: one warp per (chunk of S sorted positions, 32*VEC-wide feature slice) walks its
+//      chunk in order, gathering patch rows straight from NCHW (patchify as address arithmetic,
+//      VEC-wide loads, 8 rows in flight).  Segments that live inside one chunk are stored
+//      directly; the (at most two) segments crossing a chunk edge go to partial[chunk][slot].
+//   5. level 2: one warp per (unit, slice) adds the partials of chunk-crossing segments in chunk
+//      order, zero-fills empty units, and writes counts; a single CTA reduces the sse partials.
+// Bound: HBM -- algorithmic bytes 4*D per patch (x read once) + 8 (index) + 4*K*D (Rbar).
+#include "som_common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace som {
+
+constexpr int ACC_WARPS = 8;
+
+struct AccumPlan {
+    int64_t n;
+    int D, K;
+    int S;                 // sorted positions per chunk
+    int64_t n_chunks;
+    int n_slices_max;      // slices at VEC=1 (upper bound used for sizing)
+    int end_bit;
+    size_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_offsets, off_partial, off_sse,
+        off_cub, cub_bytes, total;
+};
+
+static int pick_chunk(int64_t n) {
+    const int64_t target = 148 * 16;
+    int S = 64;
+    while (S > 8 && n / S < target) S >>= 1;
+    return S;
+}
+
+static int make_plan(AccumPlan* pl, int64_t n, int D, int K, bool query_cub) {
+    SOM_REQUIRE(n >= 0 && n < (int64_t)INT32_MAX && D > 0 && K > 0, SOM_E_BADARG,
+                "accumulate: n=%lld D=%d K=%d out of range", (long long)n, D, K);
+    pl->n = n; pl->D = D; pl->K = K;
+    pl->S = pick_chunk(n);
+    pl->n_chunks = n > 0 ? ceil_div64(n, pl->S) : 0;
+    pl->n_slices_max = (D + 31) / 32;
+    int bits = 1;
+    while (bits < 31 && (1LL << bits) < (long long)K) ++bits;
+    pl->end_bit = bits;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    pl->off_keys_a = take((size_t)n * 4);
+    pl->off_keys_b = take((size_t)n * 4);
+    pl->off_vals_a = take((size_t)n * 4);
+    pl->off_vals_b = take((size_t)n * 4);
+    pl->off_offsets = take((size_t)(K + 1) * 4);
+    pl->off_partial = take((size_t)pl->n_chunks * 2 * D * 4);
+    pl->off_sse = take((size_t)pl->n_chunks * pl->n_slices_max * 8);
+    pl->cub_bytes = 0;
+    if (query_cub && n > 0) {
+        cub::DoubleBuffer<int> k(nullptr, nullptr), v(nullptr, nullptr);
+        size_t bytes = 0;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)n, 0, pl->end_bit);
+        if (e != cudaSuccess) { set_error("accumulate: cub size query: %s", cudaGetErrorString(e)); return (int)e; }
+        pl->cub_bytes = bytes;
+    }
+    pl->off_cub = take(pl->cub_bytes + 256);
+    pl->total = o;
+    return SOM_OK;
+}
+
+__global__ void __launch_bounds__(256) pairs_kernel(const int64_t* __restrict__ bmu, int64_t n, int K,
+                                                    int* __restrict__ keys, int* __restrict__ vals) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int64_t k = bmu[p];
+    k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+    keys[p] = (int)k;
+    vals[p] = (int)p;
+}
+
+// offsets[a] = first position whose key >= a, a in [0, K]; each boundary position p writes the
+// (possibly empty) range of unit ids between its left and right neighbour keys.
+__global__ void __launch_bounds__(256) offsets_kernel(const int* __restrict__ skey, int64_t n, int K,
+                                                      int* __restrict__ offsets) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p > n) return;
+    int lo = (p == 0) ? -1 : skey[p - 1];
+    int hi = (p == n) ? K : skey[p];
+    for (int a = lo + 1; a <= hi; ++a) offsets[a] = (int)p;
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using T = float; };
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<4> { using T = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(float (&r)[VEC], const float* p) {
+    using T = typename VecT<VEC>::T;
+    T t = __ldg(reinterpret_cast<const T*>(p));
+    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r[i] = f[i];
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&r)[VEC]) {
+    using T = typename VecT<VEC>::T;
+    T t;
+    float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) f[i] = r[i];
+    *reinterpret_cast<T*>(p) = t;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(ACC_WARPS * 32)
+seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ skey,
+                  const int* __restrict__ sid, const int* __restrict__ offsets,
+                  const float* __restrict__ Wt, float* __restrict__ Rbar,
+                  float* __restrict__ partial, double* __restrict__ sse_part,
+                  int S, int64_t n_chunks, int n_slices) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = blockIdx.x * (int64_t)ACC_WARPS + (threadIdx.x >> 5);
+    const int64_t c = wg / n_slices;
+    const int s = (int)(wg - c * n_slices);
+    if (c >= n_chunks) return;
+    const int D = g.D;
+    const int d = (s * 32 + lane) * VEC;
+    const bool act = d < D;
+    const int doff = act ? feat_off(g, d) : 0;
+    const int64_t n = g.n_patches;
+    const int64_t p0 = c * S;
+    const int64_t p1 = (p0 + S < n) ? p0 + S : n;
+
+    float acc[VEC], wt[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; wt[i] = 0.f; }
+    float sse = 0.f;
+    int cur = -1;
+    int64_t run_start = p0;
+
+    auto flush = [&](int64_t /*run_end*/) {
+        if (cur < 0 || !act) return;
+        int seg_lo = offsets[cur], seg_hi = offsets[cur + 1];
+        if (seg_lo >= p0 && seg_hi <= p1) {
+            store_vec<VEC>(Rbar + (int64_t)cur * D + d, acc);
+        } else {
+            int slot = (run_start == p0) ? 0 : 1;
+            store_vec<VEC>(partial + ((c * 2 + slot) * (int64_t)D) + d, acc);
+        }
+    };
+
+    for (int64_t p = p0; p < p1; p += 8) {
+        // lanes 0..7 fetch (key, id) and compute the patch base for the 8 positions of this group
+        int my_key = -1;
+        int64_t my_base = 0;
+        if (lane < 8 && p + lane < p1) {
+            my_key = skey[p + lane];
+            my_base = patch_base(g, (int64_t)sid[p + lane]);
+        }
+        float row[8][VEC];
+        int key[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            key[u] = __shfl_sync(0xffffffffu, my_key, u);
+            int64_t base = __shfl_sync(0xffffffffu, my_base, u);
+            if (key[u] >= 0 && act) load_vec<VEC>(row[u], x + base + doff);
+            else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) row[u][i] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (key[u] < 0) break;                    // warp-uniform: past the chunk end
+            if (key[u] != cur) {
+                flush(p + u);
+                cur = key[u];
+                run_start = p + u;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+                if (Wt != nullptr && act) load_vec<VEC>(wt, Wt + (int64_t)cur * D + d);
+            }
+            if (Wt != nullptr) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    float r = wt[i] - row[u][i];
+                    acc[i] += r;
+                    sse = fmaf(r, r, sse);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += row[u][i];
+            }
+        }
+    }
+    flush(p1);
+    if (sse_part != nullptr) {
+        float t = warp_sum(act ? sse : 0.f);
+        if (lane == 0) sse_part[c * n_slices + s] = (double)t;
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(ACC_WARPS * 32)
+seg_level2_kernel(const int* __restrict__ offsets, const float* __restrict__ partial,
+                  float* __restrict__ Rbar, int64_t* __restrict__ counts, int K, int D, int S,
+                  int n_slices) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = blockIdx.x * (int64_t)ACC_WARPS + (threadIdx.x >> 5);
+    const int64_t a = wg / n_slices;
+    const int s = (int)(wg - a * n_slices);
+    if (a >= K) return;
+    const int lo = offsets[a], hi = offsets[a + 1];
+    if (s == 0 && lane == 0 && counts != nullptr) counts[a] = (int64_t)(hi - lo);
+    const int d = (s * 32 + lane) * VEC;
+    if (d >= D) return;
+    float acc[VEC];
+    if (lo == hi) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        store_vec<VEC>(Rbar + a * D + d, acc);
+        return;
+    }
+    const int cf = lo / S, cl = (hi - 1) / S;
+    if (cf == cl) return;                              // written directly by level 1
+    const int first_slot = (lo == cf * S) ? 0 : 1;
+    load_vec<VEC>(acc, partial + (((int64_t)cf * 2 + first_slot) * D) + d);
+    int c = cf + 1;
+    for (; c + 8 <= cl + 1; c += 8) {
+        float t[8][VEC];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) load_vec<VEC>(t[u], partial + ((int64_t)(c + u) * 2 * D) + d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] += t[u][i];
+    }
+    for (; c <= cl; ++c) {
+        float t[VEC];
+        load_vec<VEC>(t, partial + ((int64_t)c * 2 * D) + d);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += t[i];
+    }
+    store_vec<VEC>(Rbar + a * D + d, acc);
+}
+
+// fixed-order double reduction of the per-(chunk, slice) squared-error partials
+__global__ void __launch_bounds__(1024) sse_reduce_kernel(const double* __restrict__ part, int64_t m,
+                                                          double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < m; i += 1024) s += part[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+template <int VEC>
+static int launch_levels(const float* x, const Geom& g, const AccumPlan& pl, const int* skey,
+                         const int* sid, const int* offsets, const float* Wt, float* Rbar,
+                         int64_t* counts, double* sse, float* partial, double* sse_part,
+                         cudaStream_t st) {
+    const int n_slices = (int)ceil_div64(g.D, 32 * VEC);
+    if (pl.n_chunks > 0) {
+        int64_t warps = pl.n_chunks * n_slices;
+        unsigned blocks = (unsigned)ceil_div64(warps, ACC_WARPS);
+        seg_level1_kernel<VEC><<<blocks, ACC_WARPS * 32, 0, st>>>(
+            x, g, skey, sid, offsets, Wt, Rbar, partial, (sse && Wt) ? sse_part : nullptr,
+            pl.S, pl.n_chunks, n_slices);
+        int rc = check_launch("seg_level1_kernel");
+        if (rc) return rc;
+    }
+    {
+        int64_t warps = (int64_t)pl.K * n_slices;
+        unsigned blocks = (unsigned)ceil_div64(warps, ACC_WARPS);
+        seg_level2_kernel<VEC><<<blocks, ACC_WARPS * 32, 0, st>>>(offsets, partial, Rbar, counts,
+                                                                 pl.K, g.D, pl.S, n_slices);
+        int rc = check_launch("seg_level2_kernel");
+        if (rc) return rc;
+    }
+    if (sse != nullptr) {
+        int64_t m = (Wt != nullptr) ? pl.n_chunks * n_slices : 0;
+        sse_reduce_kernel<<<1, 1024, 0, st>>>(sse_part, m, sse);
+        return check_launch("sse_reduce_kernel");
+    }
+    return SOM_OK;
+}
+
+}  // namespace som
+
+using namespace som;
+
+extern "C" size_t som_accumulate_workspace_bytes(int64_t n_patches, int D, int K) {
+    AccumPlan pl;
+    if (make_plan(&pl, n_patches, D, K, true) != SOM_OK) return 0;
+    return pl.total;
+}
+
+extern "C" int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH,
+                                       int pW, const int64_t* bmu, const float* Wt, int K,
+                                       float* Rbar, int64_t* counts, double* sse,
+                                       void* ws, size_t ws_bytes, void* stream) {
+    SOM_REQUIRE(x && bmu && Rbar, SOM_E_BADARG, "accumulate: null pointer");
+    SOM_REQUIRE(K > 0, SOM_E_BADARG, "accumulate: K=%d", K);
+    Geom g;
+    int rc = make_geom(&g, x, n_img, C, H, Wd, pH, pW);
+    if (rc) return rc;
+    AccumPlan pl;
+    rc = make_plan(&pl, g.n_patches, g.D, K, true);
+    if (rc) return rc;
+    SOM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, SOM_E_WORKSPACE,
+                "accumulate: workspace %zu < required %zu", ws_bytes, pl.total);
+    SOM_REQUIRE(((uintptr_t)ws & 255) == 0, SOM_E_BADARG, "accumulate: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    int* keys_a = (int*)(base + pl.off_keys_a);
+    int* keys_b = (int*)(base + pl.off_keys_b);
+    int* vals_a = (int*)(base + pl.off_vals_a);
+    int* vals_b = (int*)(base + pl.off_vals_b);
+    int* offsets = (int*)(base + pl.off_offsets);
+    float* partial = (float*)(base + pl.off_partial);
+    double* sse_part = (double*)(base + pl.off_sse);
+    void* cub_tmp = base + pl.off_cub;
+    const int64_t n = g.n_patches;
+
+    const int* skey = keys_a;
+    const int* sid = vals_a;
+    if (n > 0) {
+        pairs_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(bmu, n, K, keys_a, vals_a);
+        rc = check_launch("pairs_kernel");
+        if (rc) return rc;
+        cub::DoubleBuffer<int> kb(keys_a, keys_b), vb(vals_a, vals_b);
+        size_t bytes = pl.cub_bytes + 256;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, kb, vb, (int)n, 0, pl.end_bit, st);
+        if (e != cudaSuccess) { set_error("accumulate: radix sort: %s", cudaGetErrorString(e)); return (int)e; }
+        skey = kb.Current();
+        sid = vb.Current();
+    }
+    offsets_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, st>>>(skey, n, K, offsets);
+    rc = check_launch("offsets_kernel");
+    if (rc) return rc;
+
+    int vec = g.vec;
+    if (Wt != nullptr && ((uintptr_t)Wt & 15) != 0) vec = 1;
+    if (((uintptr_t)Rbar & 15) != 0) vec = 1;
+    if (vec == 4) return launch_levels<4>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
+    if (vec == 2) return launch_levels<2>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
+    return launch_levels<1>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
+}

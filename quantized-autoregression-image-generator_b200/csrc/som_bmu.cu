@@ -1,0 +1,54 @@
+// K1 dispatch: C-ABI entry points of the BMU search and the static variant rule.
+#include "som_common.cuh"
+
+namespace som {
+// som_bmu_ffma.cu
+size_t ffma_workspace_bytes(int64_t n_patches, int K);
+int launch_bmu_ffma(const float* x, const Geom& g, const float* W, const float* cn, int K,
+                    int64_t unit_offset, int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+// som_bmu_tc.cu
+bool tc_supported(int64_t n_patches, int D, int K);
+size_t tc_workspace_bytes(int64_t n_patches, int D, int K);
+int launch_bmu_tc(const float* x, const Geom& g, const float* W, const float* cn, int K,
+                  int64_t unit_offset, int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+}  // namespace som
+
+using namespace som;
+
+extern "C" int som_bmu_pick_variant(int64_t n_patches, int D, int K) {
+    // Static rule on the shape (no runtime autotuner): the tensor-core kernel pays a fixed
+    // operand-split pre-pass and a 128 x 256 tile, so it wants enough work to fill the machine.
+    if (tc_supported(n_patches, D, K) && n_patches >= 4096 && (int64_t)K * D >= 16384)
+        return SOM_BMU_TC3X;
+    return SOM_BMU_FFMA;
+}
+
+extern "C" size_t som_bmu_workspace_bytes(int64_t n_patches, int D, int K, int variant) {
+    if (n_patches <= 0 || D <= 0 || K <= 0) return 0;
+    if (variant == SOM_BMU_AUTO) variant = som_bmu_pick_variant(n_patches, D, K);
+    if (variant == SOM_BMU_TC3X) return tc_workspace_bytes(n_patches, D, K);
+    return ffma_workspace_bytes(n_patches, K);
+}
+
+extern "C" int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                                const float* W, const float* c_norm2, int K, int64_t unit_offset,
+                                int64_t* out_idx, float* out_rd,
+                                void* ws, size_t ws_bytes, int variant, void* stream) {
+    SOM_REQUIRE(x && W && c_norm2 && out_idx, SOM_E_BADARG, "bmu: null pointer");
+    SOM_REQUIRE(K > 0, SOM_E_BADARG, "bmu: K=%d", K);
+    SOM_REQUIRE(variant >= SOM_BMU_AUTO && variant <= SOM_BMU_TC3X, SOM_E_BADARG, "bmu: variant=%d", variant);
+    Geom g;
+    int rc = make_geom(&g, x, n_img, C, H, Wd, pH, pW);
+    if (rc) return rc;
+    if (variant == SOM_BMU_AUTO) variant = som_bmu_pick_variant(g.n_patches, g.D, K);
+    if (variant == SOM_BMU_TC3X) {
+        SOM_REQUIRE(tc_supported(g.n_patches, g.D, K), SOM_E_UNSUPPORTED,
+                    "bmu: tensor-core variant does not support D=%d K=%d", g.D, K);
+        return launch_bmu_tc(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes,
+                             (cudaStream_t)stream);
+    }
+    return launch_bmu_ffma(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes,
+                           (cudaStream_t)stream);
+}

@@ -1,0 +1,66 @@
+// Shared host/device helpers for libsomcb (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <math.h>
+
+#include "../../include/somcb.h"
+
+namespace som {
+
+// ---- error plumbing (thread-local message, codes per include/somcb.h) --------------------
+void set_error(const char* fmt, ...);
+int  fail(int code, const char* fmt, ...);
+int  check_launch(const char* what);          // cudaGetLastError -> code + message
+
+#define SOM_REQUIRE(cond, code, ...) \
+    do { if (!(cond)) return ::som::fail((code), __VA_ARGS__); } while (0)
+
+int sm_count();                                // cached per process (device 0..n: current device)
+
+// ---- patch geometry ------------------------------------------------------------------------
+// offset(p, d) = patch_base(p) + feat_off(d): patchify (models/layers.py:8-34) is separable, so
+// every kernel treats it as address arithmetic instead of materialising (N, Seq, D).
+struct Geom {
+    int64_t n_img;
+    int C, H, W, pH, pW;
+    int gH, gW;          // patches per column / row
+    int seq;             // gH * gW
+    int D;               // C * pH * pW
+    int64_t n_patches;   // n_img * seq
+    int64_t img_stride;  // C * H * W
+    int vec;             // widest aligned vector (floats) along a patch row: 4, 2 or 1
+};
+
+int make_geom(Geom* g, const void* x, int64_t n_img, int C, int H, int W, int pH, int pW);
+
+__host__ __device__ __forceinline__ int64_t patch_base(const Geom& g, int64_t p) {
+    int64_t n = p / g.seq;
+    int s = (int)(p - n * g.seq);
+    int ph = s / g.gW;
+    int pw = s - ph * g.gW;
+    return n * g.img_stride + (int64_t)(ph * g.pH) * g.W + pw * g.pW;
+}
+
+__host__ __device__ __forceinline__ int feat_off(const Geom& g, int d) {
+    if (g.seq == 1) return d;        // one patch per image: the patch row IS the image
+    int pp = g.pH * g.pW;
+    int c = d / pp;
+    int r = d - c * pp;
+    int i = r / g.pW;
+    int j = r - i * g.pW;
+    return (c * g.H + i) * g.W + j;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace som

@@ -1,0 +1,132 @@
+// K3: Gaussian neighbourhood filter along the unit axis.
+//
+//   out[a][d] = scale * sum_{t=-h..h} w(|t|) * in[a+t][d],   w(t) = expf(-( float(t*t) / two_var ))
+//
+// This is T @ in with T the K x K banded symmetric Toeplitz matrix that the reference builds
+// densely, one row per patch, in models/Codebook.py:112-125 and multiplies in :128-130
+// (forward, in = W) and in the matmul backward (in = Rbar).  Weights are generated exactly as
+// the reference does: (j-b)^2 exact in integers, converted to fp32, divided by fp32(two_var),
+// negated, expf.  The band half-width h is where expf underflows to exactly 0.
+//
+// Mapping: lane <-> feature d (coalesced 128-byte rows), each warp owns TA consecutive units
+// and slides a TA-wide window of weights held in registers over the rows j it needs, so each
+// loaded value feeds TA FFMAs and each step needs one weight from the shared table.
+// Bound: FFMA (2*K*D*band flop) -- in[] is K*D*4 bytes and stays L1/L2 resident.
+#include "som_common.cuh"
+
+namespace som {
+
+constexpr int FILT_TA = 8;          // units per warp
+constexpr int FILT_WARPS = 8;       // warps per CTA  -> 64 units x 32 features per CTA
+constexpr int FILT_PAD = FILT_TA + 8;
+
+// table layout: tab[t + off] for t in [-(h+PAD), h+PAD], zero outside [-h, h]
+__global__ void __launch_bounds__(FILT_WARPS * 32)
+filter_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int D,
+              float two_var, int h, float scale) {
+    extern __shared__ float tab[];
+    const int off = h + FILT_PAD;
+    const int tab_n = 2 * off + 1;
+    for (int i = threadIdx.x; i < tab_n; i += blockDim.x) {
+        int t = i - off;
+        int at = t < 0 ? -t : t;
+        float w = 0.f;
+        if (at <= h) {
+            float sq = (float)((long long)at * (long long)at);
+            w = expf(-(__fdiv_rn(sq, two_var)));
+        }
+        tab[i] = w;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int d = blockIdx.y * 32 + lane;
+    const int a0 = (blockIdx.x * FILT_WARPS + warp) * FILT_TA;
+    if (a0 >= K) return;
+    const bool d_ok = d < D;
+
+    float acc[FILT_TA];
+#pragma unroll
+    for (int i = 0; i < FILT_TA; ++i) acc[i] = 0.f;
+
+    // rows needed by this warp: j in [a0 - h, a0 + TA - 1 + h], clipped to [0, K)
+    int j_lo = a0 - h; if (j_lo < 0) j_lo = 0;
+    int j_hi = a0 + FILT_TA - 1 + h; if (j_hi > K - 1) j_hi = K - 1;
+
+    // window: win[i] = w(|j - (a0+i)|) = tab[(j - a0 - i) + off]
+    const float* col = in + d;
+    int j = j_lo;
+    for (; j + FILT_TA <= j_hi + 1; j += FILT_TA) {
+        float v[FILT_TA];
+#pragma unroll
+        for (int u = 0; u < FILT_TA; ++u)
+            v[u] = d_ok ? __ldg(col + (int64_t)(j + u) * D) : 0.f;
+        // weights needed in this group: t = (j+u) - (a0+i), u,i in [0,TA) -> t0-(TA-1) .. t0+(TA-1)
+        const int t0 = j - a0 + off;
+        float wv[2 * FILT_TA - 1];
+#pragma unroll
+        for (int q = 0; q < 2 * FILT_TA - 1; ++q) wv[q] = tab[t0 - (FILT_TA - 1) + q];
+#pragma unroll
+        for (int u = 0; u < FILT_TA; ++u)
+#pragma unroll
+            for (int i = 0; i < FILT_TA; ++i)
+                acc[i] = fmaf(wv[u - i + FILT_TA - 1], v[u], acc[i]);
+    }
+    for (; j <= j_hi; ++j) {
+        float v = d_ok ? __ldg(col + (int64_t)j * D) : 0.f;
+        const int t0 = j - a0 + off;
+#pragma unroll
+        for (int i = 0; i < FILT_TA; ++i) acc[i] = fmaf(tab[t0 - i], v, acc[i]);
+    }
+
+    if (d_ok) {
+#pragma unroll
+        for (int i = 0; i < FILT_TA; ++i)
+            if (a0 + i < K) out[(int64_t)(a0 + i) * D + d] = scale * acc[i];
+    }
+}
+
+// largest t with expf(-(float(t*t)/two_var)) > 0, found on the host with the same fp32 steps
+static int host_band_half_width(float two_var, int K) {
+    // expf underflows to 0 below about -103.98; search a small window around that root
+    double guess = sqrt(104.5 * (double)two_var);
+    long long t = (long long)guess + 2;
+    if (t > K) t = K;                      // rows further than K-1 apart never meet
+    while (t > 0) {
+        float sq = (float)(t * t);
+        float w = expf(-(sq / two_var));
+        if (w > 0.f) break;
+        --t;
+    }
+    return (int)t;
+}
+
+}  // namespace som
+
+using namespace som;
+
+extern "C" int som_filter_f32(const float* in, float* out, int K, int D,
+                              double neighbourhood_range, float scale, void* stream) {
+    SOM_REQUIRE(in && out, SOM_E_BADARG, "filter: null pointer");
+    SOM_REQUIRE(in != out, SOM_E_BADARG, "filter: in-place operation is not supported");
+    SOM_REQUIRE(K > 0 && D > 0, SOM_E_BADARG, "filter: K=%d D=%d", K, D);
+    SOM_REQUIRE(neighbourhood_range > 0.0, SOM_E_BADARG, "filter: neighbourhood_range=%g",
+                neighbourhood_range);
+    // models/Codebook.py:118 -- Python double arithmetic, then one rounding to fp32 at the divide
+    double variance = -(neighbourhood_range / (2.0 * log(0.1)));
+    float two_var = (float)(2.0 * variance);
+    int h = host_band_half_width(two_var, K);
+    size_t smem = (size_t)(2 * (h + FILT_PAD) + 1) * sizeof(float);
+    SOM_REQUIRE(smem <= 200 * 1024, SOM_E_SHAPE, "filter: band half-width %d too large", h);
+    static bool attr_set = false;   // idempotent; worst case it is set twice
+    if (smem > 48 * 1024 && !attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024);
+        if (e != cudaSuccess) { set_error("filter: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div64(K, FILT_WARPS * FILT_TA), (unsigned)ceil_div64(D, 32));
+    filter_kernel<<<grid, FILT_WARPS * 32, smem, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);
+    return check_launch("filter_kernel");
+}

@@ -1,0 +1,80 @@
+"""Host-buffer tokeniser: the end-to-end BMU path with HOST inputs and outputs.
+
+Models what train_quantized_transformer.py:404-421 / prune_codebook.py:133-138 do per batch
+(feature maps arrive in host memory, ``.to(device)``, get_patches_bmu, indices come back), as a
+three-stage pipeline over pinned buffers: H2D copy of chunk i+1 and D2H copy of chunk i-1 overlap
+the BMU kernel of chunk i on separate streams, ordered by events.
+"""
+import torch
+
+from . import ops as _ops
+
+
+class HostTokenizer:
+    def __init__(self, codebook, chunk_fmaps=4096, depth=3):
+        self.cb = codebook
+        self.chunk = int(chunk_fmaps)
+        self.depth = int(depth)
+        w = codebook.codebook.weight
+        if not w.is_cuda:
+            raise RuntimeError("HostTokenizer needs the codebook on a CUDA device (no CPU fallback)")
+        self.device = w.device
+        self._bufs = None
+
+    def _alloc(self, c, h, w, seq):
+        key = (c, h, w, seq)
+        if self._bufs is not None and self._bufs[0] == key:
+            return self._bufs[1]
+        dev = self.device
+        slots = []
+        for _ in range(self.depth):
+            slots.append({
+                "x": torch.empty(self.chunk, c, h, w, dtype=torch.float32, device=dev),
+                "idx": torch.empty(self.chunk * seq, dtype=torch.int64, device=dev),
+                "h2d": torch.cuda.Event(), "comp": torch.cuda.Event(), "d2h": torch.cuda.Event(),
+            })
+        streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        self._bufs = (key, (slots, streams))
+        return self._bufs[1]
+
+    @torch.no_grad()
+    def tokenize(self, fmaps_host, out_host=None):
+        """fmaps_host: (N, C, H, W) fp32 host tensor (pinned for async copies).  Returns the
+        (N, Seq) int64 host tensor of BMU indices (``out_host`` if given, pinned otherwise)."""
+        cb = self.cb
+        n, c, h, w = fmaps_host.shape
+        geom1 = _ops.geometry((1, c, h, w), cb.patch_dim)
+        seq = _ops.n_patches_of(geom1)
+        if out_host is None:
+            out_host = torch.empty(n, seq, dtype=torch.int64, pin_memory=True)
+        slots, (s_in, s_out) = self._alloc(c, h, w, seq)
+        compute = torch.cuda.current_stream(self.device)
+        weight = cb.codebook.weight.detach()
+        norms = cb._norms()
+        start = torch.cuda.Event()
+        start.record(compute)
+        s_in.wait_event(start)
+        s_out.wait_event(start)
+        n_chunks = (n + self.chunk - 1) // self.chunk
+        for i in range(n_chunks):
+            sl = slots[i % self.depth]
+            lo, hi = i * self.chunk, min(n, (i + 1) * self.chunk)
+            m = hi - lo
+            if i >= self.depth:
+                s_in.wait_event(sl["comp"])          # x slot consumed by chunk i - depth
+            with torch.cuda.stream(s_in):
+                sl["x"][:m].copy_(fmaps_host[lo:hi], non_blocking=True)
+                sl["h2d"].record(s_in)
+            compute.wait_event(sl["h2d"])
+            if i >= self.depth:
+                compute.wait_event(sl["d2h"])        # idx slot drained by chunk i - depth
+            geom = _ops.geometry((m, c, h, w), cb.patch_dim)
+            _ops.bmu(sl["x"][:m], geom, weight, norms, variant=cb.bmu_variant, out=sl["idx"][:m * seq])
+            sl["comp"].record(compute)
+            s_out.wait_event(sl["comp"])
+            with torch.cuda.stream(s_out):
+                out_host[lo:hi].view(-1).copy_(sl["idx"][:m * seq], non_blocking=True)
+                sl["d2h"].record(s_out)
+        compute.wait_stream(s_out)
+        compute.wait_stream(s_in)
+        return out_host

@@ -1,0 +1,220 @@
+"""Tensor-level wrappers over the C-ABI (include/somcb.h).
+
+PyTorch is plumbing here: it owns device memory (outputs and workspaces are torch tensors from
+the caching allocator, so they are stream-ordered and never freed under a running kernel) and
+the current CUDA stream.  All arithmetic happens inside libsomcb.  Every function raises on
+CPU tensors -- there is no fallback path.
+"""
+import torch
+
+from . import _lib
+from ._lib import SOM_BMU_AUTO, SOM_BMU_FFMA, SOM_BMU_TC3X, check  # noqa: F401
+
+
+REQUIRES_CUDA = True
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req(t, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: somcb kernels need a CUDA tensor (got {t.device}); "
+                           "there is no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def _workspace(nbytes, device):
+    if nbytes == 0:
+        return None, 0
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    return ws, int(nbytes)
+
+
+def geometry(x_shape, patch_dim):
+    """(n_img, C, H, W, pH, pW) for an NCHW batch; validates divisibility like the C side."""
+    n, c, h, w = (int(v) for v in x_shape)
+    p_h, p_w = (int(v) for v in patch_dim)
+    if h % p_h or w % p_w:
+        raise ValueError(f"image {h}x{w} is not divisible by patch {p_h}x{p_w}")
+    return n, c, h, w, p_h, p_w
+
+
+def flat_geometry(n_rows, dim):
+    """A pre-flattened (n, D) row matrix seen as n one-patch images (include/somcb.h)."""
+    return int(n_rows), 1, 1, int(dim), 1, int(dim)
+
+
+def n_patches_of(geom):
+    n, c, h, w, p_h, p_w = geom
+    return n * (h // p_h) * (w // p_w)
+
+
+def dim_of(geom):
+    n, c, h, w, p_h, p_w = geom
+    return c * p_h * p_w
+
+
+def device_info():
+    import ctypes
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib = _lib.load()
+    check("som_device_info", lib.som_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)))
+    return sm.value, major.value, minor.value
+
+
+def prepare_codebook(weight, out=None):
+    """c_norm2[j] = ||W_j||^2  (K0)."""
+    lib = _lib.load()
+    w = _req(weight, torch.float32, "weight")
+    k, d = w.shape
+    if out is None:
+        out = torch.empty(k, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        check("som_prepare_codebook_f32",
+              lib.som_prepare_codebook_f32(_ptr(w), k, d, _ptr(out), _stream(w)))
+    return out
+
+
+def bmu(x, geom, weight, c_norm2=None, unit_offset=0, want_rd=False, variant=SOM_BMU_AUTO,
+        out=None):
+    """K1.  x: fp32 contiguous buffer described by ``geom``.  Returns idx (n_patches,) int64
+    [and the reduced distance rd (n_patches,) fp32 when ``want_rd``]."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    w = _req(weight, torch.float32, "weight")
+    k, d = w.shape
+    if d != dim_of(geom):
+        raise ValueError(f"codebook dim {d} != patch dim {dim_of(geom)}")
+    npat = n_patches_of(geom)
+    if x.numel() != geom[0] * geom[1] * geom[2] * geom[3]:
+        raise ValueError("x does not match the geometry")
+    if c_norm2 is None:
+        c_norm2 = prepare_codebook(w)
+    c_norm2 = _req(c_norm2, torch.float32, "c_norm2")
+    if out is None:
+        out = torch.empty(npat, dtype=torch.int64, device=x.device)
+    rd = torch.empty(npat, dtype=torch.float32, device=x.device) if want_rd else None
+    with torch.cuda.device(x.device):
+        ws, ws_bytes = _workspace(lib.som_bmu_workspace_bytes(npat, d, k, variant), x.device)
+        check("som_bmu_nchw_f32",
+              lib.som_bmu_nchw_f32(_ptr(x), *geom, _ptr(w), _ptr(c_norm2), k, int(unit_offset),
+                                   _ptr(out), _ptr(rd), _ptr(ws), ws_bytes, variant, _stream(x)))
+    return (out, rd) if want_rd else out
+
+
+def merge_candidates(rd, idx):
+    """K1b.  rd, idx: (R, n).  Returns (idx (n,), rd (n,))."""
+    lib = _lib.load()
+    rd = _req(rd, torch.float32, "rd")
+    idx = _req(idx, torch.int64, "idx")
+    r, n = rd.shape
+    out_idx = torch.empty(n, dtype=torch.int64, device=rd.device)
+    out_rd = torch.empty(n, dtype=torch.float32, device=rd.device)
+    with torch.cuda.device(rd.device):
+        check("som_merge_candidates",
+              lib.som_merge_candidates(_ptr(rd), _ptr(idx), r, n, _ptr(out_idx), _ptr(out_rd), _stream(rd)))
+    return out_idx, out_rd
+
+
+def histogram(idx, num_units, counts=None):
+    """K5.  counts[j] += #{idx == j}; creates a zeroed int64 counts when not given."""
+    lib = _lib.load()
+    idx = _req(idx, torch.int64, "idx")
+    if counts is None:
+        counts = torch.zeros(num_units, dtype=torch.int64, device=idx.device)
+    counts = _req(counts, torch.int64, "counts")
+    with torch.cuda.device(idx.device):
+        check("som_histogram_i64",
+              lib.som_histogram_i64(_ptr(idx), idx.numel(), int(num_units), _ptr(counts), _stream(idx)))
+    return counts
+
+
+def neighbourhood_filter(inp, neighbourhood_range, scale=1.0, out=None):
+    """K3.  out = scale * T @ inp along the unit axis."""
+    lib = _lib.load()
+    inp = _req(inp, torch.float32, "inp")
+    k, d = inp.shape
+    if out is None:
+        out = torch.empty_like(inp)
+    out = _req(out, torch.float32, "out")
+    with torch.cuda.device(inp.device):
+        check("som_filter_f32",
+              lib.som_filter_f32(_ptr(inp), _ptr(out), k, d, float(neighbourhood_range), float(scale),
+                                 _stream(inp)))
+    return out
+
+
+def accumulate(x, geom, bmu_idx, table, num_units, want_counts=False, want_sse=False, out=None):
+    """K2.  Returns (Rbar (K, D), counts or None, sse (1,) float64 or None)."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    bmu_idx = _req(bmu_idx, torch.int64, "bmu")
+    d = dim_of(geom)
+    npat = n_patches_of(geom)
+    if bmu_idx.numel() != npat:
+        raise ValueError("bmu does not match the geometry")
+    if table is not None:
+        table = _req(table, torch.float32, "table")
+    if out is None:
+        out = torch.empty(num_units, d, dtype=torch.float32, device=x.device)
+    counts = torch.empty(num_units, dtype=torch.int64, device=x.device) if want_counts else None
+    sse = torch.empty(1, dtype=torch.float64, device=x.device) if want_sse else None
+    with torch.cuda.device(x.device):
+        ws, ws_bytes = _workspace(lib.som_accumulate_workspace_bytes(npat, d, int(num_units)), x.device)
+        check("som_accumulate_nchw_f32",
+              lib.som_accumulate_nchw_f32(_ptr(x), *geom, _ptr(bmu_idx), _ptr(table), int(num_units),
+                                          _ptr(out), _ptr(counts), _ptr(sse), _ptr(ws), ws_bytes,
+                                          _stream(x)))
+    return out, counts, sse
+
+
+def quantize(idx, table, geom, out=None):
+    """Gather + fused unpatchify: returns the fp32 buffer described by ``geom``."""
+    lib = _lib.load()
+    idx = _req(idx, torch.int64, "idx")
+    table = _req(table, torch.float32, "table")
+    k, d = table.shape
+    if d != dim_of(geom) or idx.numel() != n_patches_of(geom):
+        raise ValueError("idx/table do not match the geometry")
+    n, c, h, w, _, _ = geom
+    if out is None:
+        out = torch.empty(n, c, h, w, dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        check("som_quantize_nchw_f32",
+              lib.som_quantize_nchw_f32(_ptr(idx), _ptr(table), k, *geom, _ptr(out), _stream(table)))
+    return out
+
+
+def adam_step(weight, m, v, grad, lr, step, betas=(0.5, 0.999), eps=1e-8):
+    """K4, in place on weight/m/v.  ``step`` is the 1-based count after increment."""
+    lib = _lib.load()
+    for t, nm in ((weight, "weight"), (m, "m"), (v, "v"), (grad, "grad")):
+        _req(t, torch.float32, nm)
+    with torch.cuda.device(weight.device):
+        check("som_adam_f32",
+              lib.som_adam_f32(_ptr(weight), _ptr(m), _ptr(v), _ptr(grad), weight.numel(), float(lr),
+                               float(betas[0]), float(betas[1]), float(eps), int(step), _stream(weight)))
+    return weight
+
+
+def gather_rows(weight, keep):
+    lib = _lib.load()
+    w = _req(weight, torch.float32, "weight")
+    keep = _req(keep, torch.int64, "keep")
+    out = torch.empty(keep.numel(), w.shape[1], dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        check("som_gather_rows_f32",
+              lib.som_gather_rows_f32(_ptr(w), w.shape[1], _ptr(keep), keep.numel(), _ptr(out), _stream(w)))
+    return out
