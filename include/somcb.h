@@ -51,6 +51,9 @@ extern "C" {
 
 SOM_API int         som_version(void);
 SOM_API const char* som_last_error(void);
+/* Number of kernel launches this library has enqueued in this process (telemetry for bench.py;
+ * a cub radix sort counts as one). */
+SOM_API uint64_t    som_launch_count(void);
 /* SM count and compute capability of the current device (host pointers). */
 SOM_API int         som_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

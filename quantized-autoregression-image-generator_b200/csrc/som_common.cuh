@@ -13,7 +13,8 @@ namespace som {
 // ---- error plumbing (thread-local message, codes per include/somcb.h) --------------------
 void set_error(const char* fmt, ...);
 int  fail(int code, const char* fmt, ...);
-int  check_launch(const char* what);          // cudaGetLastError -> code + message
+int  check_launch(const char* what);          // cudaGetLastError -> code + message; counts launches
+unsigned long long launch_count();
 
 #define SOM_REQUIRE(cond, code, ...) \
     do { if (!(cond)) return ::som::fail((code), __VA_ARGS__); } while (0)

@@ -2,12 +2,14 @@
 // (codebook norms, candidate merge, hit histogram, quantise/gather, Adam, row compaction).
 #include "som_common.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <string.h>
 
 namespace som {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -30,8 +32,11 @@ int check_launch(const char* what) {
         set_error("%s: %s", what, cudaGetErrorString(e));
         return (int)e;
     }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return SOM_OK;
 }
+
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
     static int cached[64];
@@ -206,6 +211,8 @@ extern "C" {
 int som_version(void) { return SOM_ABI_VERSION; }
 
 const char* som_last_error(void) { return som::g_err; }
+
+uint64_t som_launch_count(void) { return som::launch_count(); }
 
 int som_device_info(int* sm, int* major, int* minor) {
     int dev = 0;

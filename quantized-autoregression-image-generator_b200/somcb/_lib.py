@@ -16,6 +16,7 @@ SOM_BMU_AUTO, SOM_BMU_FFMA, SOM_BMU_TC3X = 0, 1, 2
 SIGNATURES = {
     "som_version": (c_int, []),
     "som_last_error": (c_char_p, []),
+    "som_launch_count": (ctypes.c_uint64, []),
     "som_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "som_prepare_codebook_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "som_bmu_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),

@@ -67,11 +67,11 @@ def sharded_bmu(x, geom, weight_shard, unit_offset, group=None, ops=None, c_norm
     if world == 1:
         return idx
     n = idx.numel()
-    all_rd = torch.empty(world, n, dtype=rd.dtype, device=rd.device)
-    all_idx = torch.empty(world, n, dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(all_rd, rd, group=group)
+    all_rd = torch.empty(world * n, dtype=rd.dtype, device=rd.device)
+    all_idx = torch.empty(world * n, dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(all_rd, rd, group=group)      # rank-major: row r = rank r
     dist.all_gather_into_tensor(all_idx, idx, group=group)
-    merged, _ = ops.merge_candidates(all_rd, all_idx)
+    merged, _ = ops.merge_candidates(all_rd.view(world, n), all_idx.view(world, n))
     return merged
 
 

@@ -1,0 +1,150 @@
+"""GPU parity of the BMU search (K1) through the C-ABI, against the golden reference outputs,
+the live CPU oracle at moderate sizes, and size-independent properties at BASELINE sizes."""
+import pytest
+import torch
+
+import somcb
+from somcb import ops
+from oracle import OracleCodebook
+from oracle.step_oracle import make_oracle_codebook, synthetic_fmaps, trained_like_codebook
+from _helpers import CASES, assert_bmu_parity, flat_patches, load_case, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _variants(n_patches, d, k):
+    v = [ops.SOM_BMU_FFMA]
+    lib = somcb._lib.load()
+    if lib.som_bmu_workspace_bytes(n_patches, d, k, ops.SOM_BMU_TC3X) > 0:
+        v.append(ops.SOM_BMU_TC3X)
+    return v
+
+
+def _gpu_cb(weight, patch_dim, image_dim, channels, rng, variant=ops.SOM_BMU_AUTO):
+    cb = somcb.Codebook(patch_dim=patch_dim, image_dim=image_dim, image_channel=channels,
+                        num_embeddings=weight.shape[0], init_neighbour_range=rng)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(weight)
+    cb = cb.to(DEV)
+    cb.bmu_variant = variant
+    return cb
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_bmu_matches_reference_golden(name):
+    rec = load_case(name)
+    x = rec["x"].to(DEV)
+    flat = flat_patches(rec["x"], rec["patch_dim"])
+    for variant in _variants(flat.shape[0], flat.shape[1], rec["weight"].shape[0]) + [ops.SOM_BMU_AUTO]:
+        cb = _gpu_cb(rec["weight"], rec["patch_dim"], rec["image_dim"], rec["channels"],
+                     rec["neighbourhood_range"], variant)
+        idx = cb.get_patches_bmu(x)
+        assert idx.dtype == torch.int64 and idx.shape == rec["bmu"].shape and not idx.requires_grad
+        n_bad = assert_bmu_parity(idx, rec["bmu"], flat, rec["weight"])
+        if "trained" in name:
+            assert n_bad == 0, f"{n_bad} index mismatches on a trained-like codebook (variant {variant})"
+        assert cb.get_patches_bmu(x, reshape=True).shape == rec["bmu_reshaped"].shape
+
+
+def test_bmu_ties_resolve_to_lowest_index():
+    rec = load_golden("case_ties.pt")
+    flat = flat_patches(rec["x"], rec["patch_dim"])
+    for variant in _variants(flat.shape[0], flat.shape[1], rec["weight"].shape[0]):
+        cb = _gpu_cb(rec["weight"], rec["patch_dim"], rec["image_dim"], rec["channels"], 80, variant)
+        idx = cb.get_patches_bmu(rec["x"].to(DEV)).cpu()
+        assert int(idx.max()) < 64, "a duplicated row beat its first copy"
+        assert_bmu_parity(idx, rec["bmu"], flat, rec["weight"])
+
+
+@pytest.mark.parametrize("shape", [
+    # (fmaps, patch, K, init)                     exercises
+    (64, (2, 2), 4096, "trained"),              # BASELINE C2 shape, 16 384 patches
+    (64, (2, 2), 4096, "fresh"),
+    (32, (4, 4), 16384, "trained"),             # BASELINE C4 shape, 2 048 patches
+    (2, (4, 4), 16384, "fresh"),                # few patches, many units -> unit-split + merge
+    (16, (4, 4), 1000, "trained"),              # K not a multiple of the unit tile
+    (3, (8, 8), 777, "trained"),                # 48 patches (partial patch tile), D = 256
+    (64, (32, 32), 512, "trained"),             # BASELINE C3 shape: D = 4096, Seq = 1
+])
+def test_bmu_matches_live_oracle(shape):
+    b, pd, k, init = shape
+    x = synthetic_fmaps(b, 4242)
+    d = 4 * pd[0] * pd[1]
+    if init == "trained":
+        w = trained_like_codebook(k, pd, 7)
+    else:
+        torch.manual_seed(0)
+        w = torch.empty(k, d).uniform_(-1 / k, 1 / k)
+    oc = make_oracle_codebook(w, pd, (32, 32), 4, k // 2)
+    with torch.no_grad():
+        ref = oc.get_patches_bmu(x)
+    flat = flat_patches(x, pd)
+    for variant in _variants(flat.shape[0], d, k):
+        cb = _gpu_cb(w, pd, (32, 32), 4, k // 2, variant)
+        idx = cb.get_patches_bmu(x.to(DEV))
+        n_bad = assert_bmu_parity(idx, ref, flat, w)
+        if init == "trained":
+            assert n_bad <= max(1, flat.shape[0] // 20000), f"{n_bad} mismatches (variant {variant})"
+
+
+def test_bmu_called_in_grad_mode_on_noncontiguous_input():
+    rec = load_case("c1_trained")
+    cb = _gpu_cb(rec["weight"], rec["patch_dim"], rec["image_dim"], rec["channels"], 512)
+    x = rec["x"].to(DEV)
+    xt = x.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)      # same values, strided
+    assert not xt.is_contiguous()
+    with torch.enable_grad():
+        idx = cb.get_patches_bmu(xt, reshape=True)
+    assert idx.dtype == torch.int64 and not idx.requires_grad
+    assert_bmu_parity(idx, rec["bmu"], flat_patches(rec["x"], rec["patch_dim"]), rec["weight"])
+
+
+def test_unit_sharded_emulation_on_one_gpu():
+    """Shards are searched one after another on one device (never as concurrent waiting kernels)
+    and merged with som_merge_candidates; the result equals the unsharded search."""
+    rec = load_golden("case_ties.pt")
+    x = rec["x"].to(DEV)
+    w = rec["weight"].to(DEV)
+    geom = ops.geometry(x.shape, rec["patch_dim"])
+    full = ops.bmu(x, geom, w)
+    for world in (2, 5):
+        rds, idxs = [], []
+        for r in range(world):
+            lo, hi = somcb.shard_bounds(w.shape[0], world, r)
+            i, rd = ops.bmu(x, geom, w[lo:hi].contiguous(), unit_offset=lo, want_rd=True)
+            assert int(i.min()) >= lo and int(i.max()) < hi
+            rds.append(rd)
+            idxs.append(i)
+        merged, _ = ops.merge_candidates(torch.stack(rds), torch.stack(idxs))
+        assert torch.equal(merged, full)
+    assert_bmu_parity(full, rec["bmu"], flat_patches(rec["x"], rec["patch_dim"]), rec["weight"])
+
+
+def test_bmu_full_size_c2_properties():
+    """BASELINE config 2 at full size (39 063 fmaps -> 10 000 128 patches, D=16, K=4096):
+    batch-split invariance, histogram sum, and a 65 536-patch oracle sub-sample."""
+    pd, k = (2, 2), 4096
+    n_f = 39063
+    g = torch.Generator(device=DEV).manual_seed(123)
+    x = torch.tanh(torch.randn(n_f, 4, 32, 32, generator=g, device=DEV))
+    w = trained_like_codebook(k, pd, 7)
+    cb = _gpu_cb(w, pd, (32, 32), 4, k // 2)
+    idx = cb.get_patches_bmu(x, reshape=True)
+    assert idx.shape == (n_f, 256)
+    half = n_f // 2
+    a = cb.get_patches_bmu(x[:half].contiguous(), reshape=True)
+    b = cb.get_patches_bmu(x[half:].contiguous(), reshape=True)
+    assert torch.equal(torch.cat([a, b]), idx)
+    counts = ops.histogram(idx.reshape(-1), k)
+    assert int(counts.sum()) == n_f * 256 and int(idx.min()) >= 0 and int(idx.max()) < k
+    assert torch.equal(counts.cpu(), torch.bincount(idx.reshape(-1).cpu(), minlength=k))
+    # permutation invariance: shuffling the fmaps permutes the indices the same way
+    perm = torch.randperm(4096, device=DEV)
+    assert torch.equal(cb.get_patches_bmu(x[:4096][perm].contiguous(), reshape=True), idx[:4096][perm])
+    sub = x[-256:].cpu()                                  # 65 536 patches incl. the ragged tail
+    oc = make_oracle_codebook(w, pd, (32, 32), 4, k // 2)
+    with torch.no_grad():
+        ref = oc.get_patches_bmu(sub)
+    n_bad = assert_bmu_parity(idx[-256:].reshape(-1), ref, flat_patches(sub, pd), w)
+    assert n_bad <= 4

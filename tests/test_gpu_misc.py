@@ -1,0 +1,154 @@
+"""GPU tests of the histogram / prune path, the C-ABI error behaviour, the host-buffer pipeline
+and a literal replay of the reference scripts' call sequences on the drop-in module."""
+import ctypes
+
+import pytest
+import torch
+
+import somcb
+from somcb import _lib, ops
+from oracle.step_oracle import synthetic_fmaps, trained_like_codebook
+from _helpers import assert_bmu_parity, flat_patches, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("k,n", [(16, 1000), (4096, 1 << 20), (12288, 50000), (262144, 1 << 20)])
+def test_histogram_matches_bincount(k, n):
+    g = torch.Generator().manual_seed(k)
+    idx = torch.randint(0, k, (n,), generator=g)
+    idx[::7] = idx[0]                                    # a heavy hitter
+    counts = ops.histogram(idx.to(DEV), k)
+    assert torch.equal(counts.cpu(), torch.bincount(idx, minlength=k))
+    ops.histogram(idx.to(DEV), k, counts)                # accumulates
+    assert torch.equal(counts.cpu(), 2 * torch.bincount(idx, minlength=k))
+    bad = idx.clone()
+    bad[:10] = -1
+    bad[10:20] = k
+    c2 = ops.histogram(bad.to(DEV), k)
+    assert int(c2.sum()) == n - 20                       # out-of-range indices are ignored
+
+
+def test_prune_matches_reference_golden():
+    rec = load_golden("prune_case.pt")
+    cb = somcb.Codebook(patch_dim=rec["patch_dim"], image_dim=rec["image_dim"],
+                        image_channel=rec["channels"], num_embeddings=rec["weight"].shape[0],
+                        init_neighbour_range=128)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(rec["weight"])
+    cb = cb.to(DEV).eval()
+    batches = [synthetic_fmaps(rec["batch"], s).to(DEV) for s in rec["seeds"]]
+    counts = somcb.bmu_histogram(cb, batches)
+    assert torch.equal(counts.cpu(), rec["counts"])
+    new_cb, keep, ck = somcb.prune_codebook(cb, counts, rec["threshold"], image_channel=rec["channels"],
+                                            global_steps=17)
+    assert torch.equal(keep.cpu(), rec["good"])
+    assert torch.equal(new_cb.codebook.weight.detach().cpu(), rec["pruned_state_dict"]["codebook.weight"])
+    assert ck["num_embeddings"] == rec["good"].numel() and ck["global_steps"] == 17
+    assert list(ck["checkpoint"]) == ["codebook.weight"]
+    # the literal reference loop (prune_codebook.py:138-142) on the drop-in gives the same counts
+    total = {i: 0 for i in range(cb.num_embeddings)}
+    for fm in batches:
+        for j in cb.get_patches_bmu(fm).tolist():
+            total[j] += 1
+    assert [total[i] for i in range(cb.num_embeddings)] == rec["counts"].tolist()
+
+
+def test_merge_candidates_rule():
+    g = torch.Generator().manual_seed(1)
+    r, n = 5, 10000
+    rd = torch.randn(r, n, generator=g).round(decimals=1)         # many exact ties
+    idx = torch.stack([torch.randint(0, 1000, (n,), generator=g) + 1000 * i for i in range(r)])
+    got_i, got_rd = ops.merge_candidates(rd.to(DEV), idx.to(DEV))
+    best = rd.min(dim=0).values
+    masked = torch.where(rd == best, idx, torch.full_like(idx, 1 << 60))
+    assert torch.equal(got_i.cpu(), masked.min(dim=0).values)
+    assert torch.equal(got_rd.cpu(), best)
+
+
+def test_cabi_error_codes_and_messages():
+    lib = _lib.load()
+    x = torch.zeros(2, 4, 32, 32, device=DEV)
+    w = torch.zeros(64, 64, device=DEV)
+    cn = torch.zeros(64, device=DEV)
+    out = torch.zeros(128, dtype=torch.int64, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.som_bmu_nchw_f32(None, 2, 4, 32, 32, 4, 4, w.data_ptr(), cn.data_ptr(), 64, 0,
+                              out.data_ptr(), None, None, 0, 0, st)
+    assert rc == -1 and b"null pointer" in lib.som_last_error()
+    rc = lib.som_bmu_nchw_f32(x.data_ptr(), 2, 4, 32, 32, 5, 4, w.data_ptr(), cn.data_ptr(), 64, 0,
+                              out.data_ptr(), None, None, 0, 0, st)
+    assert rc == -2 and b"not divisible" in lib.som_last_error()
+    bmu = torch.zeros(128, dtype=torch.int64, device=DEV)
+    rbar = torch.zeros(64, 64, device=DEV)
+    ws = torch.zeros(256, dtype=torch.uint8, device=DEV)
+    rc = lib.som_accumulate_nchw_f32(x.data_ptr(), 2, 4, 32, 32, 4, 4, bmu.data_ptr(), None, 64,
+                                     rbar.data_ptr(), None, None, ws.data_ptr(), 256, st)
+    assert rc == -3 and b"workspace" in lib.som_last_error()
+    rc = lib.som_filter_f32(w.data_ptr(), w.data_ptr(), 64, 64, ctypes.c_double(4.0), ctypes.c_float(1.0), st)
+    assert rc == -1
+    with pytest.raises(_lib.SomError):
+        _lib.check("som_filter_f32", rc)
+    sm, major, _ = ops.device_info()
+    assert sm > 0 and major >= 10, "these kernels are built for sm_100a only"
+
+
+def test_cabi_raw_pointer_call_roundtrip():
+    """Call the library exactly as a foreign host would: raw device pointers and a stream."""
+    lib = _lib.load()
+    rec = load_golden("case_ties.pt")
+    x = rec["x"].to(DEV)
+    w = rec["weight"].to(DEV)
+    k, d = w.shape
+    st = torch.cuda.current_stream().cuda_stream
+    cn = torch.empty(k, device=DEV)
+    assert lib.som_prepare_codebook_f32(w.data_ptr(), k, d, cn.data_ptr(), st) == 0
+    assert torch.allclose(cn.cpu(), (rec["weight"] ** 2).sum(1), rtol=1e-6)
+    n_p = 4 * 64
+    out = torch.empty(n_p, dtype=torch.int64, device=DEV)
+    nbytes = lib.som_bmu_workspace_bytes(n_p, d, k, 0)
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=DEV)
+    rc = lib.som_bmu_nchw_f32(x.data_ptr(), 4, 4, 32, 32, 4, 4, w.data_ptr(), cn.data_ptr(), k, 0,
+                              out.data_ptr(), None, ws.data_ptr(), nbytes, 0, st)
+    assert rc == 0, lib.som_last_error()
+    assert_bmu_parity(out, rec["bmu"], flat_patches(rec["x"], rec["patch_dim"]), rec["weight"])
+
+
+def test_host_tokenizer_matches_direct_call():
+    pd, k = (2, 2), 1024
+    w = trained_like_codebook(k, pd, 7)
+    cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                        init_neighbour_range=k // 2)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(w)
+    cb = cb.to(DEV)
+    host = synthetic_fmaps(1000, 5).pin_memory()
+    tok = somcb.HostTokenizer(cb, chunk_fmaps=192, depth=3)     # ragged last chunk, slot reuse
+    got = tok.tokenize(host)
+    torch.cuda.synchronize()
+    want = cb.get_patches_bmu(host.to(DEV), reshape=True).cpu()
+    assert got.shape == (1000, 256) and torch.equal(got, want)
+    got2 = tok.tokenize(host)
+    torch.cuda.synchronize()
+    assert torch.equal(got2, want)
+
+
+def test_reference_tokenisation_call_sequence():
+    """train_quantized_transformer.py:411-421: two codebooks with different patch sizes over the
+    same fmap, called in grad mode, reshape=True."""
+    x = synthetic_fmaps(8, 9).to(DEV)
+    outs = []
+    for pd, k in (((4, 4), 512), ((2, 2), 2048)):
+        cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                            init_neighbour_range=k // 2)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(trained_like_codebook(k, pd, 3))
+        cb = cb.to(DEV)
+        cb.eval()
+        idx = cb.get_patches_bmu(x, reshape=True)
+        outs.append(idx)
+        img = cb.get_quantized_image(idx)                 # decode path (generate_images.py:225)
+        assert img.shape == x.shape
+        assert torch.equal(cb.get_patches_bmu(img, reshape=True), idx), "codec round trip"
+    assert outs[0].shape == (8, 64) and outs[1].shape == (8, 256)
