@@ -36,7 +36,7 @@ with torch.no_grad():
     ref = oc.get_patches_bmu(x[:n_check])
 flat = flat_patches(x[:n_check], pd)
 got = idx[:flat.shape[0]].cpu()
-nbad = assert_bmu_parity(got, ref, flat, w)
+nbad = -1 if os.environ.get('SOM_PROBE_NOCHECK') else assert_bmu_parity(got, ref, flat, w)
 ffma = ops.bmu(xd, geom, wd, cn, variant=ops.SOM_BMU_FFMA)
 diff = int((ffma != idx).sum())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
