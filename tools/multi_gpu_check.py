@@ -1,0 +1,83 @@
+"""N-GPU check of the multi-GPU paths over NCCL (launch with torch.distributed.run):
+  * DataParallelSom on N ranks == SomTrainer on one GPU over the full batch (replicas bit-identical)
+  * unit-sharded search (sharded_bmu) == unsharded search, sharded histogram concatenates to the full one
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "quantized-autoregression-image-generator_b200"), os.path.join(ROOT, "tests")]
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import somcb  # noqa: E402
+from somcb import ops  # noqa: E402
+from somcb.distributed import sharded_histogram  # noqa: E402
+from oracle.step_oracle import synthetic_fmaps, trained_like_codebook  # noqa: E402
+
+
+def make_cb(w, pd, dev):
+    cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=w.shape[0],
+                        init_neighbour_range=w.shape[0] // 2)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(w)
+    return cb.to(dev)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+
+    # ---- data parallel ---------------------------------------------------------------------------
+    pd, k = (4, 4), 4096
+    w0 = trained_like_codebook(k, pd, 7)
+    batch = 64 * world
+    dp_cb = make_cb(w0, pd, dev)
+    dp = somcb.DataParallelSom(dp_cb, lr=1e-4, neighbourhood_step=3)
+    dp.broadcast_weights(0)
+    ref_cb = make_cb(w0, pd, dev)
+    ref = somcb.SomTrainer(ref_cb, lr=1e-4, neighbourhood_step=3)
+    for step in range(6):
+        x = synthetic_fmaps(batch, 500 + step).to(dev)
+        l_dp = dp.step(somcb.split_batch(x, world, rank).contiguous())
+        l_ref = ref.step(x)
+        rel_l = abs(float(l_dp) - float(l_ref)) / abs(float(l_ref))
+        rel_w = float((dp_cb.codebook.weight - ref_cb.codebook.weight).norm() / ref_cb.codebook.weight.norm())
+        gathered = [torch.empty_like(dp_cb.codebook.weight.data) for _ in range(world)]
+        dist.all_gather(gathered, dp_cb.codebook.weight.data)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+        if rank == 0:
+            print(f"[dp] step {step}: loss rel {rel_l:.2e}, weights vs 1-GPU rel {rel_w:.2e}, replicas identical {same}, "
+                  f"range {dp_cb.neighbourhood_range}")
+        ok &= rel_l <= 1e-6 and rel_w <= 1e-6 and same and dp_cb.neighbourhood_range == ref_cb.neighbourhood_range
+
+    # ---- unit-sharded search + histogram ---------------------------------------------------------
+    pd, k = (8, 8), 8192
+    w = trained_like_codebook(k, pd, 3).to(dev)
+    x = synthetic_fmaps(512, 77).to(dev)
+    geom = ops.geometry(x.shape, pd)
+    full = ops.bmu(x, geom, w)
+    lo, hi = somcb.shard_bounds(k, world, rank)
+    got = somcb.sharded_bmu(x, geom, w[lo:hi].contiguous(), lo)
+    eq = bool(torch.equal(got, full))
+    mine = sharded_histogram(got, lo, hi)
+    parts = [torch.empty(somcb.shard_bounds(k, world, r)[1] - somcb.shard_bounds(k, world, r)[0],
+                         dtype=torch.int64, device=dev) for r in range(world)]
+    dist.all_gather(parts, mine)
+    hist_ok = bool(torch.equal(torch.cat(parts), ops.histogram(full, k)))
+    if rank == 0:
+        print(f"[shard] sharded_bmu == unsharded: {eq}; sharded histogram == full: {hist_ok}")
+    ok &= eq and hist_ok
+
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if int(flag) else "FAIL")
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()
