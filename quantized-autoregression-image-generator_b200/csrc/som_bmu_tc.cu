@@ -106,8 +106,23 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.  The non-suspending
+// test_wait is the fast path (the phase has usually completed already); try_wait sleeps otherwise.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_test(bar, parity)) return;
     for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
         if (spin > (1u << 20)) __trap();
 }

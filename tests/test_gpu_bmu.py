@@ -66,6 +66,9 @@ def test_bmu_ties_resolve_to_lowest_index():
     (16, (4, 4), 1000, "trained"),              # K not a multiple of the unit tile
     (3, (8, 8), 777, "trained"),                # 48 patches (partial patch tile), D = 256
     (64, (32, 32), 512, "trained"),             # BASELINE C3 shape: D = 4096, Seq = 1
+    (256, (2, 2), 4093, "trained"),             # tcgen05 config S with a ragged last unit chunk
+    (40, (4, 2), 600, "trained"),               # D = 32: config M, pW = 2 loads
+    (16, (8, 8), 2048, "trained"),              # BASELINE C5 patch size: D = 256, config L (streamed A')
 ])
 def test_bmu_matches_live_oracle(shape):
     b, pd, k, init = shape
@@ -148,3 +151,48 @@ def test_bmu_full_size_c2_properties():
         ref = oc.get_patches_bmu(sub)
     n_bad = assert_bmu_parity(idx[-256:].reshape(-1), ref, flat_patches(sub, pd), w)
     assert n_bad <= 4
+
+
+@pytest.mark.parametrize("geom", [
+    # (N, C, H, W, pH, pW, K)
+    (64, 3, 16, 16, 2, 2, 700),                 # D = 12: config S, scalar tail
+    (48, 3, 12, 18, 2, 3, 333),                 # D = 18, pW = 3: scalar loads everywhere
+    (96, 1, 16, 16, 2, 2, 512),                 # D = 4: one k-block
+    (80, 5, 8, 8, 4, 4, 260),                   # D = 80 > 73: config L with a small D
+])
+def test_bmu_generic_geometry_both_variants(geom):
+    n, c, h, w, ph, pw, k = geom
+    g = torch.Generator().manual_seed(n * k)
+    x = torch.tanh(torch.randn(n, c, h, w, generator=g))
+    d = c * ph * pw
+    flat = flat_patches(x, (ph, pw))
+    wgt = flat[torch.randperm(flat.shape[0], generator=g)[:k]].clone()
+    wgt += 0.05 * torch.randn(k, d, generator=g)
+    oc = OracleCodebook(patch_dim=(ph, pw), image_dim=(h, w), image_channel=c, num_embeddings=k,
+                        init_neighbour_range=k // 2)
+    with torch.no_grad():
+        oc.codebook.weight.copy_(wgt)
+        ref = oc.get_patches_bmu(x)
+    for variant in (ops.SOM_BMU_FFMA, ops.SOM_BMU_TC3X):
+        cb = _gpu_cb(wgt, (ph, pw), (h, w), c, k // 2, variant)
+        idx = cb.get_patches_bmu(x.to(DEV))
+        n_bad = assert_bmu_parity(idx, ref, flat, wgt)
+        assert n_bad <= 1, f"{n_bad} mismatches, variant {variant}"
+
+
+def test_tensor_core_ties_inside_and_across_chunks():
+    """Exact duplicates inside one 8-unit refine chunk, in another chunk, another 256-unit tile and
+    in the padding tail: the tensor-core variant must still return the first copy."""
+    pd = (2, 2)
+    x = synthetic_fmaps(64, 99)
+    base = trained_like_codebook(300, pd, 13)
+    w = torch.cat([base, base[:5], base[100:108], base, base[:40]], dim=0).contiguous()     # K = 653
+    oc = make_oracle_codebook(w, pd, (32, 32), 4, 300)
+    with torch.no_grad():
+        ref = oc.get_patches_bmu(x)
+    assert int(ref.max()) < 300
+    for variant in (ops.SOM_BMU_FFMA, ops.SOM_BMU_TC3X):
+        cb = _gpu_cb(w, pd, (32, 32), 4, 300, variant)
+        idx = cb.get_patches_bmu(x.to(DEV)).cpu()
+        assert int(idx.max()) < 300, f"variant {variant}: a later duplicate won"
+        assert_bmu_parity(idx, ref, flat_patches(x, pd), w)
