@@ -77,6 +77,7 @@ struct Params {
     const float* W;         // config S refine: original codebook rows, ||c||^2, unit count
     const float* cn;
     int K;
+    int dbg;                // SOM_TC_DEBUG bit mask (timing experiments only; results are wrong)
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -249,6 +250,8 @@ __device__ __forceinline__ void load_row(float (&xr)[DCAP], const float* src, bo
     }
 }
 
+__device__ long long g_tl[5][64];
+
 // ---- the GEMM + argmin kernel ----------------------------------------------------------------------
 // R      patch tiles per super-tile (resident A' slots)
 // EXACT  epilogue resolves the index in registers (else: winning CHUNK-unit chunk, refined by builders)
@@ -263,6 +266,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     __shared__ float mrg_val[TM];
     __shared__ int mrg_idx[TM];
     __shared__ int foff_s[FUSED ? DCAP : 1];
+    long long (*tl)[64] = g_tl;                             // PROF: timeline of 64 consecutive tiles (CTA 0)
+    (void)tl;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -305,6 +310,11 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     for (int g = 0; g < groups; ++g) {
                         mbar_wait(&bars.empty[stage], phase ^ 1);
                         uint8_t* sbase = ring + (size_t)stage * P.stage_bytes;
+                        if ((P.dbg & 4) && (st != (int)blockIdx.x || n * groups + g >= P.n_stages)) {
+                            mbar_arrive(&bars.full[stage]);
+                            if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         mbar_expect_tx(&bars.full[stage], P.stage_bytes);
                         for (int j = 0; j < P.stage_kb; ++j)
                             tma_load_2d(&map_b, &bars.full[stage], sbase + (size_t)j * B_BLK_BYTES,
@@ -339,15 +349,16 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (r < r_eff) {
-                            if (PROF) c0 = clock64();
-                            if (n == 0) mbar_wait(&bars.a_full[r], a_fpar);
+                            if (PROF) { c0 = clock64(); const long long ti = pt[2] - 480; if (blockIdx.x == 0 && ti >= 0 && ti < 64) tl[0][ti] = c0; }
+                            if (n == 0 && !(P.dbg & 16)) mbar_wait(&bars.a_full[r], a_fpar);
                             mbar_wait(&bars.acc_empty[acc], acc_phase ^ 1);
                             tc_fence_after();
                             if (PROF) { pt[0] += clock64() - c0; c0 = clock64(); }
                             issue_tile<8>(tmem_base + (uint32_t)acc * TN, adesc[r], bd, P.ksteps);
                             tc_commit(&bars.acc_full[acc]);
                             if (n == P.NT - 1) tc_commit(&bars.a_empty[r]);       // slot free early
-                            if (PROF) { pt[1] += clock64() - c0; ++pt[2]; }
+                            if (PROF) { pt[1] += clock64() - c0; ++pt[2];
+                                        const long long ti = pt[2] - 1 - 480; if (blockIdx.x == 0 && ti >= 0 && ti < 64) { tl[1][ti] = c0; tl[2][ti] = clock64(); } }
                             acc ^= 1;
                             acc_phase ^= (acc == 0);
                         }
@@ -356,6 +367,12 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
                 }
                 a_fpar ^= 1;
+            }
+            if (PROF && blockIdx.x == 0) {
+                __threadfence();
+                for (int i = 0; i < 64; ++i)
+                    printf("[tl] tile %d mma_wait_begin %lld issue_begin %lld issue_end %lld | epi_full_seen %lld epi_arrive %lld\n", i,
+                           tl[0][i] - tl[0][0], tl[1][i] - tl[0][0], tl[2][i] - tl[0][0], tl[3][i] - tl[0][0], tl[4][i] - tl[0][0]);
             }
             if (PROF && blockIdx.x % 21 == 0 && pt[2] > 0)
                 printf("[bmu_tc mma] tiles=%lld cyc/tile total=%lld waits=%lld issue+commit=%lld\n", pt[2],
@@ -404,7 +421,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         }
     } else if (warp >= BUILD_WARP0 && warp < BUILD_WARP0 + BUILD_WARPS) {
         // ================================ A' builders (+ config S refine) ==============
-        if (FUSED) {
+        if (FUSED && !(P.dbg & 16)) {
             const int t = threadIdx.x - BUILD_WARP0 * 32;       // patch row inside the tile
             const int D = P.g.D;
             const int vec = P.g.vec;
@@ -492,7 +509,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         mbar_wait(&bars.a_empty[r], a_epar);
                         if (PROF) { bt[0] += clock64() - b0; b0 = clock64(); }
                         uint8_t* slot = a_res + (size_t)r * P.KB * A_BLK_BYTES;
-                        if ((D & 3) == 0) {
+                        if ((P.dbg & 2) && st != (int)blockIdx.x) {
+                        } else if ((D & 3) == 0) {
                             // 16-byte chunks: chunk q of the row lands at ((q & 7) ^ (t & 7)) inside its
                             // 128-byte swizzle row -- 8 consecutive rows fill one conflict-free wavefront
                             const int dq = D >> 2;
@@ -532,13 +550,13 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     }
                 }
                 a_epar ^= 1;
-                prefetch(st + gridDim.x);            // rows of the next super-tile, a full tile time ahead
+                if (!(P.dbg & 8)) prefetch(st + gridDim.x);            // rows of the next super-tile, a full tile time ahead
                 long long b1 = PROF ? clock64() : 0;
-                if (!EXACT && st_prev >= 0) refine_super(st_prev);
+                if (!EXACT && st_prev >= 0 && !(P.dbg & 1)) refine_super(st_prev);
                 if (PROF) bt[2] += clock64() - b1;
                 st_prev = st;
             }
-            if (!EXACT && st_prev >= 0) refine_super(st_prev);
+            if (!EXACT && st_prev >= 0 && !(P.dbg & 1)) refine_super(st_prev);
             if (PROF && blockIdx.x == 0 && t == 0 && bt[3] > 0)
                 printf("[bmu_tc bld ] slots=%lld cyc/slot wait_a_empty=%lld write=%lld refine(per super-tile incl wait)=%lld\n",
                        bt[3], bt[0] / bt[3], bt[1] / bt[3], bt[2] * R / bt[3]);
@@ -565,7 +583,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         long long e0 = PROF ? clock64() : 0;
                         mbar_wait(&bars.acc_full[acc], acc_phase);
                         tc_fence_after();
-                        if (PROF) { et[0] += clock64() - e0; e0 = clock64(); }
+                        if (PROF) { et[0] += clock64() - e0; e0 = clock64();
+                                    const long long ti = et[2] - 480; if (blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && ti >= 0 && ti < 64) tl[3][ti] = e0; }
                         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * TN + half * 128);
                         const int col0 = n * TN + half * 128;
                         uint32_t va[32], vb[32];
@@ -606,6 +625,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars.acc_empty[acc]);
+                        if (PROF) { const long long ti = et[2] - 480; if (blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && ti >= 0 && ti < 64) tl[4][ti] = clock64(); }
                         consume(vb, 3);
                         if (PROF) { et[1] += clock64() - e0; ++et[2]; }
                         acc ^= 1;
@@ -616,7 +636,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             // merge the two column halves (value asc, index asc) and store, one patch tile at a time
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if (r < r_eff) {
+                if (r < r_eff && !(P.dbg & 32)) {
                     if (half == 1) { mrg_val[row] = best[r]; mrg_idx[row] = bidx[r]; }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (half == 0) {
@@ -760,6 +780,7 @@ static void make_plan(Plan* pl, int64_t n, int D, int K) {
     if (pl->KB <= 2 && D <= DCAP_S) {
         pl->cfg = CFG_S;
         pl->a_resident = 1; pl->stage_kb = pl->KB; pl->n_stages = 2; pl->R = MAX_R;
+        { const char* e = getenv("SOM_TC_R1"); if (e && e[0] == '1') pl->R = 1; }
         pl->stage_bytes = (uint32_t)pl->KB * B_BLK_BYTES;
         pl->a_bytes = (uint32_t)pl->R * pl->KB * A_BLK_BYTES;
     } else if (pl->KB <= 7 && D <= DCAP_M) {
@@ -861,6 +882,7 @@ int launch_bmu_tc(const float* x, const Geom& g, const float* W, const float* cn
     P.stage_kb = pl.stage_kb; P.n_stages = pl.n_stages; P.unit_offset = unit_offset;
     P.a_bytes = pl.a_bytes; P.stage_bytes = pl.stage_bytes;
     P.x = x; P.g = g; P.W = W; P.cn = cn; P.K = K;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SOM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
 
     if (pl.cfg != CFG_L) {
         // fused builders: one launch over all patches, no operand round trip through memory
@@ -874,6 +896,7 @@ int launch_bmu_tc(const float* x, const Geom& g, const float* W, const float* cn
         if (pl.cfg == CFG_S) {
             static int prof = -1;       // SOM_TC_PROFILE=1: per-role cycle breakdown printed by CTA 0
             if (prof < 0) { const char* e = getenv("SOM_TC_PROFILE"); prof = (e && e[0] == '1') ? 1 : 0; }
+            if (pl.R == 1) return launch_gemm<1, false, true, DCAP_S, true>(map_a, map_b, P, pl.smem_bytes, grid, st);
             if (prof) return launch_gemm<MAX_R, false, true, DCAP_S, true>(map_a, map_b, P, pl.smem_bytes, grid, st);
             return launch_gemm<MAX_R, false, true, DCAP_S>(map_a, map_b, P, pl.smem_bytes, grid, st);
         }
