@@ -31,6 +31,7 @@
 //   L  larger D: both operands stream through a 4-stage ring; A' comes from a pre-pass split kernel
 // Bound: tensor pipe at TF32 rate / 3 -- algorithmic 2*K*D flop per patch.
 #include "som_common.cuh"
+#include "som_tc_ptx.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -39,11 +40,6 @@ namespace som {
 
 namespace tc {
 
-constexpr int TM = 128;              // patches per MMA tile (UMMA M)
-constexpr int TN = 256;              // units per MMA tile (UMMA N)
-constexpr int KBLK = 32;             // floats per k-block: one 128-byte swizzle row
-constexpr int A_BLK_BYTES = TM * KBLK * 4;     // 16 KB
-constexpr int B_BLK_BYTES = TN * KBLK * 4;     // 32 KB
 constexpr int NUM_THREADS = 448;
 constexpr int BUILD_WARP0 = 2, BUILD_WARPS = 4;
 constexpr int EPI_WARP0 = 6, EPI_THREADS = 256;
@@ -53,9 +49,6 @@ constexpr int CHUNK = 8;             // units per refine chunk (config S)
 constexpr int DCAP_S = 20, DCAP_M = 76;
 constexpr uint32_t SMEM_LIMIT = 232448;        // 227 KB
 constexpr uint32_t STATIC_SMEM = 2048;         // barriers + merge buffers + feature offsets (upper bound)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
-                           ((uint32_t)(TM >> 4) << 24);
-constexpr float PAD_NORM = 1.0e30f;            // ||c||^2 of padding units: never the minimum
 
 struct Params {
     int KB;                 // k-blocks per row (KP / 32)
@@ -80,121 +73,6 @@ struct Params {
     int dbg;                // SOM_TC_DEBUG bit mask (timing experiments only; results are wrong)
 };
 
-// ---- PTX helpers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.  The non-suspending
-// test_wait is the fast path (the phase has usually completed already); try_wait sleeps otherwise.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_test(bar, parity)) return;
-    for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
-        if (spin > (1u << 20)) __trap();
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accum)
-        : "memory");
-}
-// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4
-// | version=1 | layout_type=2.  Advancing one K=8 step inside the 128-byte row adds 32 B (2 units).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-#define SOM_R32(a) "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), \
-    "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),           \
-    "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),         \
-    "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
-#define SOM_RW32(a) "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), \
-    "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),           \
-    "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]),         \
-    "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
-
-// asynchronous TMEM load of 32 consecutive columns of this warp's 32 lanes (no wait)
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : SOM_R32(r)
-        : "r"(taddr)
-        : "memory");
-}
-// wait for all outstanding TMEM loads; the "+r" operands pin every use of r[] after the wait
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : SOM_RW32(r)::"memory");
-}
-__device__ __forceinline__ float min32(const uint32_t (&r)[32]) {
-    float m = __uint_as_float(r[0]);
-#pragma unroll
-    for (int i = 1; i < 32; ++i) m = fminf(m, __uint_as_float(r[i]));
-    return m;
-}
-__device__ __forceinline__ int first_eq32(const uint32_t (&r)[32], float m) {
-    int q = 31;
-#pragma unroll
-    for (int i = 30; i >= 0; --i) q = (__uint_as_float(r[i]) == m) ? i : q;
-    return q;
-}
-__device__ __forceinline__ float tf32_rna(float v) {
-    uint32_t o;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
-    return __uint_as_float(o);
-}
-
 struct __align__(8) Barriers {
     uint64_t full[MAX_STAGES];
     uint64_t empty[MAX_STAGES];
@@ -218,35 +96,6 @@ __device__ __forceinline__ void issue_tile(uint32_t d_addr, uint64_t adesc, uint
             const uint32_t ob = (uint32_t)(((ks >> 2) * B_BLK_BYTES + (ks & 3) * 32) >> 4);
             tc_mma_tf32(d_addr, adesc + oa, bdesc + ob, ks > 0 ? 1u : 0u);
         }
-    }
-}
-
-// builder-side loader: D features of patch row `src` into registers (static indexing, DCAP >= D)
-template <int DCAP>
-__device__ __forceinline__ void load_row(float (&xr)[DCAP], const float* src, bool ok, int D, int vec,
-                                         const int* foff) {
-#pragma unroll
-    for (int d = 0; d < DCAP; d += 4) {
-        float tmp[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ok && d < D) {
-            if (vec == 4) {
-                float4 v = __ldg(reinterpret_cast<const float4*>(src + foff[d]));
-                tmp[0] = v.x; tmp[1] = v.y; tmp[2] = v.z; tmp[3] = v.w;
-            } else if (vec == 2) {
-                float2 v0 = __ldg(reinterpret_cast<const float2*>(src + foff[d]));
-                tmp[0] = v0.x; tmp[1] = v0.y;
-                if (d + 2 < D) {
-                    float2 v1 = __ldg(reinterpret_cast<const float2*>(src + foff[d + 2]));
-                    tmp[2] = v1.x; tmp[3] = v1.y;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (d + e < D) tmp[e] = __ldg(src + foff[d + e]);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) xr[d + e] = tmp[e];
     }
 }
 
@@ -726,36 +575,6 @@ __global__ void __launch_bounds__(256) split_x_kernel(const float* __restrict__ 
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-        return nullptr;
-    fn = (EncodeTiledFn)p;
-    return fn;
-}
-
-static int make_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, uint32_t box_rows) {
-    EncodeTiledFn fn = get_encode_fn();
-    SOM_REQUIRE(fn != nullptr, SOM_E_UNSUPPORTED, "bmu(tc): cuTensorMapEncodeTiled is not available");
-    cuuint64_t dims[2] = {kp, rows};
-    cuuint64_t strides[1] = {kp * 4};
-    cuuint32_t box[2] = {KBLK, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SOM_REQUIRE(r == CUDA_SUCCESS, SOM_E_UNSUPPORTED, "bmu(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return SOM_OK;
-}
-
 enum Config { CFG_S = 0, CFG_M = 1, CFG_L = 2 };
 
 struct Plan {
@@ -829,6 +648,17 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const Param
 
 }  // namespace tc
 
+// som_bmu_tc_s.cu: config S (D <= 16)
+bool tc_s_applicable(int D);
+size_t tc_s_workspace_bytes(int64_t n_patches, int D, int K);
+int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
+                    int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, cudaStream_t st);
+static bool use_s4(int D) {
+    static int old = -1;            // SOM_TC_OLD_S=1: previous config-S kernel (A/B comparisons only)
+    if (old < 0) { const char* e = getenv("SOM_TC_OLD_S"); old = (e && e[0] == '1') ? 1 : 0; }
+    return !old && tc_s_applicable(D);
+}
+
 bool tc_supported(int64_t n_patches, int D, int K) {
     if (n_patches <= 0 || D <= 0 || K <= 0) return false;
     if (n_patches / tc::TM >= (1ll << 30)) return false;
@@ -847,6 +677,7 @@ bool tc_supported(int64_t n_patches, int D, int K) {
 
 size_t tc_workspace_bytes(int64_t n_patches, int D, int K) {
     if (!tc_supported(n_patches, D, K)) return 0;
+    if (use_s4(D)) return tc_s_workspace_bytes(n_patches, D, K);
     tc::Plan pl;
     tc::make_plan(&pl, n_patches, D, K);
     return pl.total;
@@ -858,6 +689,7 @@ int launch_bmu_tc(const float* x, const Geom& g, const float* W, const float* cn
     using namespace tc;
     const int64_t n = g.n_patches;
     if (n == 0) return SOM_OK;
+    if (use_s4(g.D)) return launch_bmu_tc_s(x, g, W, cn, K, unit_offset, out_idx, out_rd, ws, ws_bytes, st);
     Plan pl;
     make_plan(&pl, n, g.D, K);
     SOM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, SOM_E_WORKSPACE,

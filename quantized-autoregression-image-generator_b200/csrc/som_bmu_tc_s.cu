@@ -1,0 +1,520 @@
+// K1 (tensor-core variant), small patch dimension D <= 16 ("config S"): BMU search as an
+// error-compensated 3xTF32 GEMM on tcgen05 with the argmin fused into the TMEM epilogue.  sm_100a only.
+//
+// Replaces patchify + torch.cdist + torch.argmin of Codebook.get_patches_bmu
+// (/root/reference/models/Codebook.py:77-99) for fine patches (BASELINE config 2: P=2, D=16, K=4096).
+//
+// Reduced distance rd[p][j] = ||c_j||^2 - 2 x_p . c_j (the row constant ||x_p||^2 is dropped).
+// With hi = RNA-rounded TF32 part and lo = TF32-rounded remainder of a value:
+//     rd = n1+n2+n3  - 2 x_hi.c_hi  - 2 x_lo.c_hi  - 2 x_hi.c_lo          (lo.lo dropped: 2^-24 relative)
+// Operands are stored ONCE (hi | lo in one 128-byte swizzled row) and the three products are three
+// groups of tcgen05.mma k-steps that start at different 32-byte offsets inside the same rows:
+//     A row (patch)  = [ x_hi (Dp) | x_lo (Dp) ]           B row (unit) = [ -2c_hi (Dp) | -2c_lo (Dp) ]
+//     tail k-step    : A = [1 1 1 0 0 0 0 0]   B = [n1 n2 n3 0 0 0 0 0]   (32-byte rows, SWIZZLE_32B)
+// so a 128 x 256 tile costs 3*Dp/8 + 1 MMAs of K=8 (7 for D = 16) and a unit tile is 40 KB in shared memory.
+//
+// One persistent CTA per SM, 448 threads, warp-specialised:
+//   warp 0      TMA producer: unit tiles (32 KB block + 8 KB tail) into a 3-stage mbarrier ring
+//   warp 1      MMA issuer  : one thread, M128 x N256 x K8 kind::tf32, two TMEM accumulator stages.  The
+//                             barrier checks for the NEXT tile are made before the LAST MMA of the current
+//                             tile is issued: the issue queue is shallow (measured: the thread runs at most
+//                             1-2 MMAs ahead of the pipe), so anything between two tiles is exposed otherwise.
+//   warps 2-5   builders    : read patch rows from NCHW (patchify = address arithmetic, prefetched one
+//                             super-tile ahead), split hi/lo and write the swizzled A rows of R = 4 resident
+//                             patch tiles; then resolve the BMU inside the winning 8-unit chunk of the
+//                             previous super-tile with exact fp32 FFMA scores (batched, latency-tolerant loads)
+//   warps 6-13  epilogue    : tcgen05.ld 32x32b.x32 of their TMEM lane quarter / column half, running
+//                             (min, 8-unit chunk) per patch row -- under one ALU op per distance; the N x K
+//                             distance matrix never leaves TMEM
+// Every streamed unit tile feeds R = 4 patch tiles.  Bound: tensor pipe (TF32 rate / 3).
+#include "som_common.cuh"
+#include "som_tc_ptx.cuh"
+
+#include <stdlib.h>
+
+namespace som {
+namespace tcs {
+using namespace tc;
+
+constexpr int R = 4;                         // resident patch tiles per super-tile
+constexpr int NSTAGE = 3;                    // unit-tile ring stages
+constexpr int BUILD_WARP0 = 2, BUILD_WARPS = 4;
+constexpr int EPI_WARP0 = 6, EPI_WARPS = 8;
+constexpr int NUM_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;       // 448
+constexpr int CHUNK = 8;                     // units per refine chunk
+constexpr int DMAX = 16;
+constexpr int TAIL_A_BYTES = TM * 32;        // 4 KB
+constexpr int TAIL_B_BYTES = TN * 32;        // 8 KB
+constexpr int STAGE_BYTES = B_BLK_BYTES + TAIL_B_BYTES;         // 40 KB
+constexpr int TILES_BYTES = R * A_BLK_BYTES + TAIL_A_BYTES + NSTAGE * STAGE_BYTES;   // 188 KB
+
+struct Params {
+    int nks;                // k-steps per product group: Dp / 8
+    int NT;                 // unit tiles
+    int n_mtiles;           // patch tiles
+    int64_t rows;           // valid patches
+    int64_t unit_offset;
+    int64_t* out_idx;
+    float* out_rd;
+    const float* x;
+    Geom g;
+    const float* W;
+    const float* cn;
+    int K;
+    int dbg;
+};
+
+struct __align__(8) Barriers {
+    uint64_t full[NSTAGE], empty[NSTAGE];
+    uint64_t a_full[R], a_empty[R];
+    uint64_t acc_full[2], acc_empty[2];
+    uint64_t ref_full[2];
+    uint32_t tmem_base, pad;
+};
+struct Aux {
+    Barriers bars;
+    float mrg_val[R][TM];
+    int mrg_idx[R][TM];
+    int cbase[2][R][TM];
+    int foff[DMAX];
+};
+constexpr uint32_t SMEM_BYTES = 1024 + TILES_BYTES + sizeof(Aux);
+
+// K-major SWIZZLE_32B operand descriptor: 32-byte rows, 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) |
+           (6ull << 61);
+}
+
+__device__ long long g_prof[4];              // CTA 0: cycles of the MMA loop, tiles issued
+__device__ long long g_tl6[2][64];
+__device__ long long g_tl[6][64];            // SOM_TC_DEBUG & 64: timeline of tiles 200..263 of CTA 0
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_slots = tiles;
+    uint8_t* a_tail = tiles + R * A_BLK_BYTES;
+    uint8_t* ring = a_tail + TAIL_A_BYTES;
+    Aux& aux = *reinterpret_cast<Aux*>(ring + NSTAGE * STAGE_BYTES);
+    Barriers& bars = aux.bars;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+        for (int r = 0; r < R; ++r) { mbar_init(&bars.a_full[r], BUILD_WARPS); mbar_init(&bars.a_empty[r], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars.acc_full[a], 1); mbar_init(&bars.acc_empty[a], EPI_WARPS); }
+        mbar_init(&bars.ref_full[0], EPI_WARPS / 2);
+        mbar_init(&bars.ref_full[1], EPI_WARPS / 2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int d = threadIdx.x; d < P.g.D; d += NUM_THREADS) aux.foff[d] = feat_off(P.g, d);
+    if (threadIdx.x < TM) {
+        // constant tail operand: row t = [1 1 1 0 | 0 0 0 0] in the 32-byte swizzle (chunk ^= bit 2 of t)
+        const int t = threadIdx.x;
+        const uint32_t sw = (uint32_t)(t >> 2) & 1u;
+        float4* rowp = reinterpret_cast<float4*>(a_tail + t * 32);
+        rowp[sw] = make_float4(1.f, 1.f, 1.f, 0.f);
+        rowp[sw ^ 1u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+    const int n_super = (P.n_mtiles + R - 1) / R;
+    const int nks = P.nks;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+                for (int n = 0; n < P.NT; ++n) {
+                    mbar_wait(&bars.empty[stage], phase ^ 1);
+                    uint8_t* sbase = ring + (size_t)stage * STAGE_BYTES;
+                    mbar_expect_tx(&bars.full[stage], STAGE_BYTES);
+                    tma_load_2d(&map_b, &bars.full[stage], sbase, 0, n * TN);
+                    tma_load_2d(&map_t, &bars.full[stage], sbase + B_BLK_BYTES, 0, n * TN);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        // The whole warp runs this loop: warp-uniform control flow keeps the operand descriptors in uniform
+        // registers (a lane-0-only branch costs ~140 cycles per MMA issue in R2UR/vote sequences, this ~50);
+        // one elected lane issues the tcgen05 ops.  The issue queue holds ~4 MMAs, so the barrier check,
+        // fence and commit of a tile hide behind the previous tile as long as the loop stays lean.
+        const bool leader = elect_one();
+        const uint64_t adesc0 = umma_desc(smem_u32(a_slots));
+        const uint64_t atdesc = umma_desc_sw32(smem_u32(a_tail));
+        const uint64_t bdesc0 = umma_desc(smem_u32(ring));
+        const uint64_t btdesc0 = umma_desc_sw32(smem_u32(ring + B_BLK_BYTES));
+        constexpr uint32_t STAGE_UNITS = (uint32_t)STAGE_BYTES >> 4;
+        constexpr uint32_t SLOT_UNITS = (uint32_t)A_BLK_BYTES >> 4;
+        int stage = 0;
+        uint32_t phase = 0, a_par = 0, j = 0;
+        const long long t_begin = clock64();
+        for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+            const int r_eff = min(R, P.n_mtiles - st * R);
+            for (int n = 0; n < P.NT; ++n) {
+                mbar_wait(&bars.full[stage], phase);
+                const uint64_t bd = bdesc0 + (uint32_t)stage * STAGE_UNITS;
+                const uint64_t btd = btdesc0 + (uint32_t)stage * STAGE_UNITS;
+                for (int r = 0; r < r_eff; ++r) {
+                    if (n == 0) mbar_wait(&bars.a_full[r], a_par);
+                    mbar_wait(&bars.acc_empty[j & 1u], ((j >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_addr = tmem_base + (j & 1u) * TN;
+                    const uint64_t ad = adesc0 + (uint32_t)r * SLOT_UNITS;
+                    if (leader) {
+                        // norm tail first, then hi.hi, lo.hi, hi.lo
+                        tc_mma_tf32(d_addr, atdesc, btd, 0u);
+#pragma unroll
+                        for (int ks = 0; ks < DMAX / 8; ++ks)
+                            if (ks < nks) tc_mma_tf32(d_addr, ad + 2u * ks, bd + 2u * ks, 1u);
+#pragma unroll
+                        for (int ks = 0; ks < DMAX / 8; ++ks)
+                            if (ks < nks) tc_mma_tf32(d_addr, ad + 2u * (nks + ks), bd + 2u * ks, 1u);
+#pragma unroll
+                        for (int ks = 0; ks < DMAX / 8; ++ks)
+                            if (ks < nks) tc_mma_tf32(d_addr, ad + 2u * ks, bd + 2u * (nks + ks), 1u);
+                        tc_commit(&bars.acc_full[j & 1u]);
+                        if (n == P.NT - 1) tc_commit(&bars.a_empty[r]);
+                    }
+                    ++j;
+                }
+                if (leader) tc_commit(&bars.empty[stage]);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            a_par ^= 1;
+        }
+        if (blockIdx.x == 0 && leader && j > 0) { g_prof[0] = clock64() - t_begin; g_prof[1] = (long long)j; }
+    } else if (warp >= BUILD_WARP0 && warp < BUILD_WARP0 + BUILD_WARPS) {
+        // ================================ A builders + chunk refine =====================
+        const int t = threadIdx.x - BUILD_WARP0 * 32;       // patch row inside a tile
+        const int D = P.g.D;
+        const int vec = P.g.vec;
+        const int Dp = nks * 8;
+        const uint32_t row_off = (uint32_t)t * 128u;
+        const uint32_t sw = (uint32_t)(t & 7);
+        const bool v4 = ((D & 3) == 0);
+        const bool w4 = v4 && ((reinterpret_cast<uintptr_t>(P.W) & 15) == 0);
+        float xv[R][DMAX];
+        auto prefetch = [&](int st_next) {
+            const int r_nxt = (st_next < n_super) ? min(R, P.n_mtiles - st_next * R) : 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t p = (int64_t)(st_next * R + r) * TM + t;
+                const bool ok = (r < r_nxt) && (p < P.rows);
+                load_row<DMAX>(xv[r], P.x + (ok ? patch_base(P.g, p) : 0), ok, D, vec, aux.foff);
+            }
+        };
+        // exact fp32 scores of the CHUNK candidates of one row, four candidates' loads in flight at a time;
+        // strict '>' in ascending unit order keeps the lowest index on ties (same arithmetic as the FFMA variant)
+        auto refine_row = [&](int64_t p, int u0) {
+            float xr[DMAX];
+            load_row<DMAX>(xr, P.x + patch_base(P.g, p), true, D, vec, aux.foff);
+            if (u0 < 0 || u0 >= P.K) u0 = 0;           // defensive: the epilogue only writes bases in [0, K_pad)
+            float best = -INFINITY;
+            int bu = u0;
+#pragma unroll
+            for (int h = 0; h < CHUNK; h += 4) {
+                float wr[4][DMAX];
+                float accv[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int u = u0 + h + c;
+                    const bool ok = u < P.K;
+                    const float* wp = P.W + (int64_t)(ok ? u : 0) * D;
+                    accv[c] = ok ? -0.5f * __ldg(P.cn + u) : -INFINITY;
+#pragma unroll
+                    for (int d = 0; d < DMAX; d += 4) {
+                        if (d < D) {
+                            if (w4) {
+                                const float4 q = __ldg(reinterpret_cast<const float4*>(wp + d));
+                                wr[c][d] = q.x; wr[c][d + 1] = q.y; wr[c][d + 2] = q.z; wr[c][d + 3] = q.w;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) wr[c][d + e] = (d + e < D) ? __ldg(wp + d + e) : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) wr[c][d + e] = 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float a = accv[c];
+#pragma unroll
+                    for (int d = 0; d < DMAX; ++d)
+                        if (d < D) a = fmaf(xr[d], wr[c][d], a);
+                    if (a > best) { best = a; bu = u0 + h + c; }
+                }
+            }
+            P.out_idx[p] = (int64_t)bu + P.unit_offset;
+            if (P.out_rd) P.out_rd[p] = -2.0f * best;
+        };
+        auto refine_super = [&](int st_done, int it_done) {
+            mbar_wait_warp<true>(&bars.ref_full[it_done & 1], (uint32_t)(it_done >> 1) & 1u, lane);
+            const int r_done = min(R, P.n_mtiles - st_done * R);
+            for (int r = 0; r < r_done; ++r) {
+                const int64_t p = (int64_t)(st_done * R + r) * TM + t;
+                if (p < P.rows) refine_row(p, aux.cbase[it_done & 1][r][t]);
+            }
+        };
+
+        prefetch(blockIdx.x);
+        uint32_t a_epar = 1;
+        int st_prev = -1, it = 0;
+        for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+            const int r_eff = min(R, P.n_mtiles - st * R);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r < r_eff) {
+                    mbar_wait_warp<true>(&bars.a_empty[r], a_epar, lane);
+                    uint8_t* slot = a_slots + (size_t)r * A_BLK_BYTES + row_off;
+                    if (v4) {
+                        // 16-byte chunk q of the row lands at (q ^ (t & 7)): 8 consecutive rows fill one
+                        // conflict-free shared-memory wavefront
+                        const int dq = Dp >> 2;
+#pragma unroll
+                        for (int d4 = 0; d4 < DMAX / 4; ++d4) {
+                            if (d4 < dq) {
+                                float4 hi, lo;
+                                hi.x = tf32_rna(xv[r][4 * d4]);     lo.x = tf32_rna(xv[r][4 * d4] - hi.x);
+                                hi.y = tf32_rna(xv[r][4 * d4 + 1]); lo.y = tf32_rna(xv[r][4 * d4 + 1] - hi.y);
+                                hi.z = tf32_rna(xv[r][4 * d4 + 2]); lo.z = tf32_rna(xv[r][4 * d4 + 2] - hi.z);
+                                hi.w = tf32_rna(xv[r][4 * d4 + 3]); lo.w = tf32_rna(xv[r][4 * d4 + 3] - hi.w);
+                                *reinterpret_cast<float4*>(slot + ((((uint32_t)d4) ^ sw) << 4)) = hi;
+                                *reinterpret_cast<float4*>(slot + ((((uint32_t)(dq + d4)) ^ sw) << 4)) = lo;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < DMAX; ++d) {
+                            if (d < Dp) {
+                                const float v = xv[r][d];           // zero beyond D (load_row)
+                                const float hi = tf32_rna(v);
+                                const float lo = tf32_rna(v - hi);
+                                const uint32_t kh = (uint32_t)d, kl = (uint32_t)(Dp + d);
+                                *reinterpret_cast<float*>(slot + ((((kh >> 2) ^ sw) << 4) | ((kh & 3u) << 2))) = hi;
+                                *reinterpret_cast<float*>(slot + ((((kl >> 2) ^ sw) << 4) | ((kl & 3u) << 2))) = lo;
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.a_full[r]);
+                }
+            }
+            a_epar ^= 1;
+            if (st_prev >= 0 && !(P.dbg & 1)) refine_super(st_prev, it - 1);
+            prefetch(st + gridDim.x);                // rows of the next super-tile, most of a super-tile ahead
+            st_prev = st;
+        }
+        if (st_prev >= 0 && !(P.dbg & 1)) refine_super(st_prev, it - 1);
+    } else if (warp >= EPI_WARP0) {
+        // ================================ epilogue ====================================
+        const int ew = warp - EPI_WARP0;            // 0..7
+        const int half = ew >> 2;                   // column half of the accumulator
+        const int lg = warp & 3;                    // TMEM lane quarter this warp may access
+        const int row = lg * 32 + lane;             // patch row inside the tile
+        uint32_t j = 0;
+        int it = 0;
+        for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+            const int r_eff = min(R, P.n_mtiles - st * R);
+            float best[R];
+            int bidx[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { best[r] = INFINITY; bidx[r] = 0; }
+            for (int n = 0; n < P.NT; ++n) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r < r_eff) {
+                        const uint32_t acc = j & 1u;
+                        mbar_wait(&bars.acc_full[acc], (j >> 1) & 1u);
+                        tc_fence_after();
+                        const bool tlrec = (P.dbg & 64) && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && j >= 200 && j < 264;
+                        if (tlrec) g_tl[4][j - 200] = clock64();
+                        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TN + (uint32_t)half * 128u;
+                        const int col0 = n * TN + half * 128;
+                        uint32_t va[32], vb[32];
+                        // minimum per CHUNK(8)-column group; only (min, chunk) is tracked
+                        auto consume = [&](const uint32_t (&v)[32], int c) {
+                            float q[4];
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                float m8 = __uint_as_float(v[g * 8]);
+#pragma unroll
+                                for (int i = 1; i < 8; ++i) m8 = fminf(m8, __uint_as_float(v[g * 8 + i]));
+                                q[g] = m8;
+                            }
+                            const float m = fminf(fminf(q[0], q[1]), fminf(q[2], q[3]));
+                            if (m < best[r]) {
+                                best[r] = m;
+                                const int sub = (q[0] == m) ? 0 : (q[1] == m) ? 1 : (q[2] == m) ? 2 : 3;
+                                bidx[r] = col0 + c * 32 + sub * CHUNK;
+                            }
+                        };
+                        tmem_ld32_issue(taddr, va);
+                        tmem_ld_wait(va);
+                        tmem_ld32_issue(taddr + 32, vb);
+                        consume(va, 0);
+                        tmem_ld_wait(vb);
+                        tmem_ld32_issue(taddr + 64, va);
+                        consume(vb, 1);
+                        tmem_ld_wait(va);
+                        tmem_ld32_issue(taddr + 96, vb);
+                        consume(va, 2);
+                        tmem_ld_wait(vb);
+                        // accumulator fully read: hand it back before the last reduction
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars.acc_empty[acc]);
+                        if (tlrec) g_tl[5][j - 200] = clock64();
+                        consume(vb, 3);
+                        ++j;
+                    }
+                }
+            }
+            // merge the two column halves (value asc, index asc); the chunk bases go to the builders
+            if (half == 1) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) { aux.mrg_val[r][row] = best[r]; aux.mrg_idx[r][row] = bidx[r]; }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r < r_eff) {
+                        const float ov = aux.mrg_val[r][row];
+                        const int oi = aux.mrg_idx[r][row];
+                        int bi = bidx[r];
+                        if (ov < best[r] || (ov == best[r] && oi < bi)) bi = oi;
+                        aux.cbase[it & 1][r][row] = bi;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.ref_full[it & 1]);       // release: chunk bases visible
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// B rows [-2 hi(c) (Dp) | -2 lo(c) (Dp) | 0..] (32 floats) and tail rows [n1 n2 n3 0 0 0 0 0]; rows >= K are
+// padding units whose norm can never be the minimum
+__global__ void __launch_bounds__(256) split_w_s_kernel(const float* __restrict__ W, const float* __restrict__ cn,
+                                                        int K, int D, int Dp, int K_pad, float* __restrict__ Bp,
+                                                        float* __restrict__ Tp) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)K_pad * 40) return;
+    const int row = (int)(t / 40);
+    const int c = (int)(t - (int64_t)row * 40);
+    if (c < 32) {
+        float out = 0.f;
+        if (row < K && c < 2 * Dp) {
+            const int d = (c < Dp) ? c : c - Dp;
+            if (d < D) {
+                const float w = W[(int64_t)row * D + d];
+                const float hi = tf32_rna(w);
+                out = -2.0f * (c < Dp ? hi : tf32_rna(w - hi));
+            }
+        }
+        Bp[(int64_t)row * 32 + c] = out;
+    } else {
+        const int k = c - 32;
+        float out = 0.f;
+        if (row < K) {
+            const float nrm = cn[row];
+            const float n1 = tf32_rna(nrm);
+            const float n2 = tf32_rna(nrm - n1);
+            const float n3 = tf32_rna(nrm - n1 - n2);
+            out = (k == 0) ? n1 : (k == 1) ? n2 : (k == 2) ? n3 : 0.f;
+        } else if (k == 0) {
+            out = PAD_NORM;
+        }
+        Tp[(int64_t)row * 8 + k] = out;
+    }
+}
+
+}  // namespace tcs
+
+bool tc_s_applicable(int D) { return D >= 1 && D <= tcs::DMAX; }
+
+size_t tc_s_workspace_bytes(int64_t n_patches, int D, int K) {
+    (void)n_patches; (void)D;
+    const size_t K_pad = (size_t)(K + tc::TN - 1) / tc::TN * tc::TN;
+    return align_up(K_pad * 32 * 4, 1024) + align_up(K_pad * 8 * 4, 1024);
+}
+
+int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
+                    int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, cudaStream_t st) {
+    using namespace tcs;
+    const int64_t n = g.n_patches;
+    if (n == 0) return SOM_OK;
+    const int D = g.D;
+    const int Dp = (D + 7) / 8 * 8;
+    const int K_pad = (K + TN - 1) / TN * TN;
+    const size_t need = tc_s_workspace_bytes(n, D, K);
+    SOM_REQUIRE(ws != nullptr && ws_bytes >= need, SOM_E_WORKSPACE, "bmu(tc): workspace %zu < required %zu", ws_bytes, need);
+    SOM_REQUIRE(((uintptr_t)ws & 255) == 0, SOM_E_BADARG, "bmu(tc): workspace must be 256-byte aligned");
+    float* Bp = (float*)ws;
+    float* Tp = (float*)((char*)ws + align_up((size_t)K_pad * 32 * 4, 1024));
+    {
+        const int64_t items = (int64_t)K_pad * 40;
+        split_w_s_kernel<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(W, cn, K, D, Dp, K_pad, Bp, Tp);
+        int rc = check_launch("split_w_s_kernel");
+        if (rc) return rc;
+    }
+    CUtensorMap map_b, map_t;
+    int rc = make_map2d(&map_b, Bp, (uint64_t)K_pad, 32, 128, 32, TN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map2d(&map_t, Tp, (uint64_t)K_pad, 8, 32, 8, TN, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+
+    Params P;
+    P.nks = Dp / 8; P.NT = K_pad / TN; P.n_mtiles = (int)ceil_div64(n, TM); P.rows = n;
+    P.unit_offset = unit_offset; P.out_idx = out_idx; P.out_rd = out_rd;
+    P.x = x; P.g = g; P.W = W; P.cn = cn; P.K = K;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SOM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(bmu_tc_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_done = true;
+    }
+    const int n_super = (P.n_mtiles + R - 1) / R;
+    const int grid = n_super < sm_count() ? n_super : sm_count();
+    bmu_tc_s_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
+    return check_launch("bmu_tc_s_kernel");
+}
+
+}  // namespace som
+
+// debug: cycles spent by CTA 0's MMA issue loop and the tiles it issued in the last config-S launch
+extern "C" SOM_API int som_debug_tc_timeline(long long* out512) {
+    cudaMemcpyFromSymbol(out512 + 384, som::tcs::g_tl6, 2 * 64 * sizeof(long long));
+    return (int)cudaMemcpyFromSymbol(out512, som::tcs::g_tl, 6 * 64 * sizeof(long long));
+}
+extern "C" SOM_API int som_debug_tc_cycles(long long* out2) {
+    return (int)cudaMemcpyFromSymbol(out2, som::tcs::g_prof, 2 * sizeof(long long));
+}

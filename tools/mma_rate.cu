@@ -388,6 +388,63 @@ __global__ void __launch_bounds__(128, 1) queue_probe(long long* out) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
 }
+
+// issue-queue probe 2: [7 dependent MMAs + commit] x 4 tiles alternating accumulators; timestamps after every op
+__global__ void __launch_bounds__(128, 1) queue_probe2(long long* out, int same_acc) {
+    extern __shared__ uint8_t raw[];
+    __shared__ uint64_t bar[4];
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* tiles = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<float*>(tiles)[i] = 1.0f;
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((128u >> 4) << 24);
+    if (warp == 0 && lane == 0) {
+        const uint64_t ad = umma_desc(smem_u32(tiles)), bd = umma_desc(smem_u32(tiles + 16384));
+        long long ts[40];
+        int k = 0;
+        ts[k++] = clock64();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tmem + (same_acc ? 0 : (t & 1) * 256)), "l"(ad + (uint32_t)((i & 3) * 2)), "l"(bd + (uint32_t)((i & 3) * 2)), "r"(idesc), "r"(i > 0 ? 1u : 0u) : "memory");
+                ts[k++] = clock64();
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[t])) : "memory");
+            ts[k++] = clock64();
+        }
+        mbar_wait(&bar[3], 0);
+        ts[k++] = clock64();
+        for (int i = 0; i < k; ++i) out[i] = ts[i] - ts[0];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+static void run_probe2(int same_acc) {
+    long long* out; cudaMalloc(&out, 40 * 8);
+    cudaFuncSetAttribute(queue_probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
+    for (int rep = 0; rep < 2; ++rep) { queue_probe2<<<1, 128, 60000>>>(out, same_acc); cudaDeviceSynchronize(); }
+    long long h[40]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("probe2 (same_acc=%d): per tile [7 MMA issue stamps | commit stamp]; last = completion\n", same_acc);
+    for (int t = 0; t < 4; ++t) { for (int i = 0; i < 8; ++i) printf(" %lld%s", h[1 + t * 8 + i], i == 6 ? " |" : ""); printf("\n"); }
+    printf(" done %lld\n", h[33]);
+}
+
 static void run_probe() {
     long long* out; cudaMalloc(&out, 26 * 8);
     cudaFuncSetAttribute(queue_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
@@ -436,6 +493,8 @@ static void run(const char* name, int kblocks) {
 
 int main() {
     run_probe();
+    run_probe2(0);
+    run_probe2(1);
     run<1, 256, 0>("tf32 cg1 SS N=256", 2);
     run<1, 256, 0>("tf32 cg1 SS N=256", 4);
     run<1, 128, 0>("tf32 cg1 SS N=128", 2);

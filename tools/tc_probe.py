@@ -43,12 +43,26 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 for _ in range(2):
     ops.bmu(xd, geom, wd, cn, variant=variant)
 e0.record()
-reps = 5
+reps = int(os.environ.get('SOM_PROBE_REPS', '5'))
 for _ in range(reps):
     ops.bmu(xd, geom, wd, cn, variant=variant)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 npat = idx.numel()
+try:
+    import ctypes
+    cyc = (ctypes.c_longlong * 2)()
+    lib = somcb._lib.load()
+    if lib.som_debug_tc_cycles(cyc) == 0 and cyc[1] > 0 and d <= 16 and variant == 2:
+        print(f"  [config S] CTA0 MMA loop: {cyc[0] / cyc[1]:.0f} cycles per 128x256 tile over {cyc[1]} tiles", flush=True)
+    if os.environ.get("SOM_TC_DEBUG") and int(os.environ["SOM_TC_DEBUG"]) & 64:
+        tl = (ctypes.c_longlong * 512)()
+        lib.som_debug_tc_timeline(tl)
+        t0 = tl[0]
+        for i in range(40):
+            print(f"  [tl] tile {i}: iter_begin {tl[i]-t0} tests_begin {tl[64+i]-t0} tests_done {tl[384+i]-t0} last_mma_issued {tl[448+i]-t0} committed {tl[128+i]-t0} ok={tl[192+i]} | epi_full_seen {tl[256+i]-t0} epi_arrive {tl[320+i]-t0}")
+except Exception as e:  # noqa: BLE001
+    print("  (no cycle probe:", e, ")")
 print(f"  OK: {nbad} near-tie diffs vs oracle on {flat.shape[0]} patches, {diff} diffs vs FFMA on {npat}; "
       f"{ms:.3f} ms -> {npat / ms * 1e3:.3e} patches/s, {2.0 * k * d * npat / ms / 1e9:.1f} TFLOP/s", flush=True)
