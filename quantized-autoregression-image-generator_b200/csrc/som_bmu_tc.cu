@@ -226,46 +226,47 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             if (PROF && blockIdx.x % 21 == 0 && pt[2] > 0)
                 printf("[bmu_tc mma] tiles=%lld cyc/tile total=%lld waits=%lld issue+commit=%lld\n", pt[2],
                        (clock64() - pt_begin) / pt[2], pt[0] / pt[2], pt[1] / pt[2]);
-        } else if (lane == 0) {
+        } else if (P.stage_kb != P.KB) {
+            // configs M / L.  The whole warp runs the loop (warp-uniform control flow keeps the operand
+            // descriptors in uniform registers -- a lane-0-only branch costs ~3x more per MMA issue); one
+            // elected lane issues the tcgen05 instructions.
+            const bool leader = elect_one();
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, a_fpar = 0;
-            // operand descriptors are fixed per slot / ring stage: build them once
-            uint64_t adesc[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) adesc[r] = umma_desc(smem_u32(a_res + (size_t)r * P.KB * A_BLK_BYTES));
+            const uint64_t adesc0 = umma_desc(smem_u32(a_res));
             const uint64_t bdesc0 = umma_desc(smem_u32(ring));
             const uint32_t stage_units = P.stage_bytes >> 4;
             const uint32_t a_in_stage = (uint32_t)B_BLK_BYTES >> 4;      // config L: A' block after B' block
-            {
-              for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+            for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
                 for (int n = 0; n < P.NT; ++n) {
-                    {
-                        // one k-block per stage, one patch tile per super-tile
-                        if (FUSED && n == 0) mbar_wait(&bars.a_full[0], a_fpar);
-                        mbar_wait(&bars.acc_empty[acc], acc_phase ^ 1);
+                    // one k-block per stage, one patch tile per super-tile
+                    if (FUSED && n == 0) mbar_wait(&bars.a_full[0], a_fpar);
+                    mbar_wait(&bars.acc_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_addr = tmem_base + (uint32_t)acc * TN;
+                    for (int kb = 0; kb < P.KB; ++kb) {
+                        mbar_wait(&bars.full[stage], phase);
                         tc_fence_after();
-                        const uint32_t d_addr = tmem_base + (uint32_t)acc * TN;
-                        for (int kb = 0; kb < P.KB; ++kb) {
-                            mbar_wait(&bars.full[stage], phase);
-                            tc_fence_after();
-                            const uint64_t bdesc = bdesc0 + (uint32_t)stage * stage_units;
-                            const uint64_t ad = FUSED ? adesc[0] + (uint32_t)kb * ((uint32_t)A_BLK_BYTES >> 4)
-                                                      : bdesc + a_in_stage;
-                            const int nk = min(4, P.ksteps - kb * 4);
+                        const uint64_t bdesc = bdesc0 + (uint32_t)stage * stage_units;
+                        const uint64_t ad = FUSED ? adesc0 + (uint32_t)kb * ((uint32_t)A_BLK_BYTES >> 4)
+                                                  : bdesc + a_in_stage;
+                        const int nk = min(4, P.ksteps - kb * 4);
+                        if (leader) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 if (k < nk) tc_mma_tf32(d_addr, ad + 2u * k, bdesc + 2u * k, (kb | k) != 0);
                             tc_commit(&bars.empty[stage]);
-                            if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
                         }
+                        if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                    if (leader) {
                         tc_commit(&bars.acc_full[acc]);
                         if (FUSED && n == P.NT - 1) tc_commit(&bars.a_empty[0]);
-                        acc ^= 1;
-                        acc_phase ^= (acc == 0);
                     }
+                    acc ^= 1;
+                    acc_phase ^= (acc == 0);
                 }
                 a_fpar ^= 1;
-              }
             }
         }
     } else if (warp >= BUILD_WARP0 && warp < BUILD_WARP0 + BUILD_WARPS) {
@@ -653,6 +654,18 @@ bool tc_s_applicable(int D);
 size_t tc_s_workspace_bytes(int64_t n_patches, int D, int K);
 int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
                     int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, cudaStream_t st);
+// som_bmu_tc_l.cu: config L (streamed operands, fused builders, optional split-K)
+size_t tc_l_workspace_bytes(int64_t n_patches, int D, int K);
+int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
+                    int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_l_splits(int64_t n_patches, int D, int K);
+static bool use_l2(int64_t n_patches, int D, int K) {
+    static int mode = -1;           // SOM_TC_L=0: never, 2: always (A/B comparisons only); default: split-K shapes
+    if (mode < 0) { const char* e = getenv("SOM_TC_L"); mode = e ? atoi(e) : 1; }
+    const int kb = (3 * D + 3 + tc::KBLK - 1) / tc::KBLK;
+    if (mode == 0 || (kb <= 7 && D <= tc::DCAP_M)) return false;
+    return mode == 2 || tc_l_splits(n_patches, D, K) > 1;
+}
 static bool use_s4(int D) {
     static int old = -1;            // SOM_TC_OLD_S=1: previous config-S kernel (A/B comparisons only)
     if (old < 0) { const char* e = getenv("SOM_TC_OLD_S"); old = (e && e[0] == '1') ? 1 : 0; }
@@ -678,6 +691,7 @@ bool tc_supported(int64_t n_patches, int D, int K) {
 size_t tc_workspace_bytes(int64_t n_patches, int D, int K) {
     if (!tc_supported(n_patches, D, K)) return 0;
     if (use_s4(D)) return tc_s_workspace_bytes(n_patches, D, K);
+    if (use_l2(n_patches, D, K)) return tc_l_workspace_bytes(n_patches, D, K);
     tc::Plan pl;
     tc::make_plan(&pl, n_patches, D, K);
     return pl.total;
@@ -690,6 +704,7 @@ int launch_bmu_tc(const float* x, const Geom& g, const float* W, const float* cn
     const int64_t n = g.n_patches;
     if (n == 0) return SOM_OK;
     if (use_s4(g.D)) return launch_bmu_tc_s(x, g, W, cn, K, unit_offset, out_idx, out_rd, ws, ws_bytes, st);
+    if (use_l2(n, g.D, K)) return launch_bmu_tc_l(x, g, W, cn, K, unit_offset, out_idx, out_rd, ws, ws_bytes, st);
     Plan pl;
     make_plan(&pl, n, g.D, K);
     SOM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, SOM_E_WORKSPACE,

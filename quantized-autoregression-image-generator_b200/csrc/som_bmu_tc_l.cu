@@ -1,0 +1,576 @@
+// K1 (tensor-core variant), large patch dimension ("config L": D too large for a resident patch tile):
+// BMU search as an error-compensated 3xTF32 GEMM on tcgen05, both operands streamed.  sm_100a only.
+//
+// Replaces patchify + torch.cdist + torch.argmin of Codebook.get_patches_bmu
+// (/root/reference/models/Codebook.py:77-99) for coarse patches: BASELINE config 3 (whole-fmap codebook,
+// D = 4096, K = 512, 4096 patches) and config 5 (D = 256, K = 32 768 per GPU).
+//
+//     rd[p][j] = ||c_j||^2 - 2 x_p . c_j = n1+n2+n3 - 2 x_hi.c_hi - 2 x_lo.c_hi - 2 x_hi.c_lo
+// (hi = RNA TF32 part, lo = TF32-rounded remainder; the dropped lo.lo term is 2^-24 relative).  The feature
+// axis is cut into 32-feature blocks; per block the hi and lo parts are stored ONCE and feed three groups of
+// K=8 MMAs:  A_hi x B_hi,  A_lo x B_hi,  A_hi x B_lo.  The norms enter through one extra K=8 step
+// (A = [1 1 1 0..], B = [n1 n2 n3 0..], 32-byte rows, SWIZZLE_32B).
+//
+// One persistent CTA per SM, 448 threads, warp-specialised:
+//   warp 0      TMA producer: B_hi / B_lo blocks (256 units x 32 features, 32 KB) of the pre-split codebook
+//                             into a 4-stage ring, norm tails into a 2-stage ring
+//   warp 1      MMA issuer  : warp-uniform loop, one elected lane issues M128 x N256 x K8 kind::tf32 into
+//                             two TMEM accumulator stages
+//   warps 2-9   builders    : two groups of four warps alternate feature blocks: a thread reads the 32 features
+//                             of its patch row straight from NCHW (patchify = address arithmetic, the next block's
+//                             loads in flight while the current one is converted), splits hi/lo and writes both
+//                             swizzled 16 KB operand blocks of its A-ring slot -- no pre-pass, no operand copy in HBM
+//   warps 10-13 epilogue    : tcgen05.ld of their TMEM lane quarter, all 256 columns
+// Two epilogue modes (static rule on the shape):
+//   ARGMIN   enough patch tiles to fill the machine: running exact (min, index) per patch row over all unit
+//            tiles -- the N x K distance matrix never leaves TMEM
+//   SPLIT-K  few patch tiles (config 3: 32 tiles, 2 unit tiles, 128 feature blocks): the feature axis is
+//            split over S CTAs per patch tile, partial distances (S x N x K fp32, 8 MB per split at config 3)
+//            go to a workspace and a small kernel adds them in fixed order and takes the argmin
+// Bound: tensor pipe (TF32 rate / 3); per feature block the CTA moves 64 KB of B and 16 KB of x.
+#include "som_common.cuh"
+#include "som_tc_ptx.cuh"
+
+#include <stdlib.h>
+
+namespace som {
+namespace tcl {
+using namespace tc;
+
+constexpr int NA = 2;                        // A ring slots (hi + lo block)
+constexpr int NB = 4;                        // B ring stages (one 32 KB block)
+constexpr int BUILD_WARP0 = 2, BUILD_WARPS = 8;             // two groups of 4 warps, alternate feature blocks
+constexpr int EPI_WARP0 = 10, EPI_WARPS = 4;
+constexpr int NUM_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;       // 448
+constexpr int A_SLOT_BYTES = 2 * A_BLK_BYTES;                   // 32 KB
+constexpr int TAIL_A_BYTES = TM * 32;        // 4 KB
+constexpr int TAIL_B_BYTES = TN * 32;        // 8 KB
+constexpr int FOFF_MAX = 1024;               // feature-offset table entries kept in shared memory
+constexpr int MAX_SPLIT = 8;
+constexpr int TILES_BYTES = NA * A_SLOT_BYTES + NB * B_BLK_BYTES + TAIL_A_BYTES + 2 * TAIL_B_BYTES;   // 212 KB
+
+struct Params {
+    int DB;                 // 32-feature blocks
+    int nks_last;           // k-steps of the last block
+    int NT;                 // unit tiles
+    int n_mtiles;           // patch tiles
+    int S;                  // feature splits (1: ARGMIN epilogue)
+    int fb_per_split;
+    int K_pad;
+    int64_t rows;           // valid patches
+    int64_t unit_offset;
+    int64_t* out_idx;
+    float* out_rd;
+    float* partial;         // [S][n_mtiles * 128][K_pad]   (S > 1)
+    const float* x;
+    Geom g;
+    int dbg;                // SOM_TC_DEBUG (timing experiments only)
+};
+
+struct __align__(8) Barriers {
+    uint64_t b_full[NB], b_empty[NB];
+    uint64_t t_full[2], t_empty[2];
+    uint64_t a_full[NA], a_empty[NA];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base, pad;
+};
+struct Aux {
+    Barriers bars;
+    int foff[FOFF_MAX];
+};
+constexpr uint32_t SMEM_BYTES = 1024 + TILES_BYTES + sizeof(Aux);
+
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) |
+           (6ull << 61);
+}
+
+template <bool SPLITK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_ring = tiles;
+    uint8_t* b_ring = a_ring + NA * A_SLOT_BYTES;
+    uint8_t* a_tail = b_ring + NB * B_BLK_BYTES;
+    uint8_t* t_ring = a_tail + TAIL_A_BYTES;
+    Aux& aux = *reinterpret_cast<Aux*>(t_ring + 2 * TAIL_B_BYTES);
+    Barriers& bars = aux.bars;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int D = P.g.D;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NB; ++s) { mbar_init(&bars.b_full[s], 1); mbar_init(&bars.b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.t_full[s], 1); mbar_init(&bars.t_empty[s], 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(&bars.a_full[s], BUILD_WARPS / 2); mbar_init(&bars.a_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars.acc_full[a], 1); mbar_init(&bars.acc_empty[a], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (D <= FOFF_MAX)
+        for (int d = threadIdx.x; d < D; d += NUM_THREADS) aux.foff[d] = feat_off(P.g, d);
+    if (threadIdx.x < TM) {
+        // constant tail operand: row t = [1 1 1 0 | 0 0 0 0] in the 32-byte swizzle (chunk ^= bit 2 of t)
+        const int t = threadIdx.x;
+        const uint32_t sw = (uint32_t)(t >> 2) & 1u;
+        float4* rowp = reinterpret_cast<float4*>(a_tail + t * 32);
+        rowp[sw] = make_float4(1.f, 1.f, 1.f, 0.f);
+        rowp[sw ^ 1u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+    const int n_jobs = P.n_mtiles * P.S;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int bs = 0, ts = 0;
+            uint32_t b_ph = 0, t_ph = 0;
+            for (int q = blockIdx.x; q < n_jobs; q += gridDim.x) {
+                const int s = q % P.S;
+                const int fb0 = s * P.fb_per_split;
+                const int fb1 = min(P.DB, fb0 + P.fb_per_split);
+                for (int n = 0; n < P.NT; ++n) {
+                    if (s == 0) {
+                        mbar_wait(&bars.t_empty[ts], t_ph ^ 1);
+                        mbar_expect_tx(&bars.t_full[ts], TAIL_B_BYTES);
+                        tma_load_2d(&map_t, &bars.t_full[ts], t_ring + ts * TAIL_B_BYTES, 0, n * TN);
+                        if (++ts == 2) { ts = 0; t_ph ^= 1; }
+                    }
+                    for (int fb = fb0; fb < fb1; ++fb) {
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {          // hi block, then lo block
+                            mbar_wait(&bars.b_empty[bs], b_ph ^ 1);
+                            mbar_expect_tx(&bars.b_full[bs], B_BLK_BYTES);
+                            tma_load_2d(&map_b, &bars.b_full[bs], b_ring + (size_t)bs * B_BLK_BYTES,
+                                        (part * P.DB + fb) * KBLK, n * TN);
+                            if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        // warp-uniform control flow (operand descriptors stay in uniform registers); one elected lane issues
+        const bool leader = elect_one();
+        const uint64_t adesc0 = umma_desc(smem_u32(a_ring));
+        const uint64_t bdesc0 = umma_desc(smem_u32(b_ring));
+        const uint64_t atdesc = umma_desc_sw32(smem_u32(a_tail));
+        const uint64_t btdesc0 = umma_desc_sw32(smem_u32(t_ring));
+        constexpr uint32_t A_SLOT_UNITS = (uint32_t)A_SLOT_BYTES >> 4;
+        constexpr uint32_t A_LO_UNITS = (uint32_t)A_BLK_BYTES >> 4;
+        constexpr uint32_t B_UNITS = (uint32_t)B_BLK_BYTES >> 4;
+        constexpr uint32_t T_UNITS = (uint32_t)TAIL_B_BYTES >> 4;
+        int as = 0, bs = 0, ts = 0;
+        uint32_t a_ph = 0, b_ph = 0, t_ph = 0, j = 0;
+        for (int q = blockIdx.x; q < n_jobs; q += gridDim.x) {
+            const int s = q % P.S;
+            const int fb0 = s * P.fb_per_split;
+            const int fb1 = min(P.DB, fb0 + P.fb_per_split);
+            for (int n = 0; n < P.NT; ++n) {
+                mbar_wait(&bars.acc_empty[j & 1u], ((j >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (j & 1u) * TN;
+                uint32_t accum = 0;
+                if (s == 0) {
+                    mbar_wait(&bars.t_full[ts], t_ph);
+                    tc_fence_after();
+                    if (leader) {
+                        tc_mma_tf32(d_addr, atdesc, btdesc0 + (uint32_t)ts * T_UNITS, 0u);
+                        tc_commit(&bars.t_empty[ts]);
+                    }
+                    accum = 1;
+                    if (++ts == 2) { ts = 0; t_ph ^= 1; }
+                }
+                for (int fb = fb0; fb < fb1; ++fb) {
+                    const int nks = (fb == P.DB - 1) ? P.nks_last : 4;
+                    const uint64_t ahi = adesc0 + (uint32_t)as * A_SLOT_UNITS;
+                    const uint64_t alo = ahi + A_LO_UNITS;
+                    mbar_wait(&bars.a_full[as], a_ph);
+                    mbar_wait(&bars.b_full[bs], b_ph);
+                    tc_fence_after();
+                    uint64_t bd = bdesc0 + (uint32_t)bs * B_UNITS;
+                    if (leader) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < nks) tc_mma_tf32(d_addr, ahi + 2u * k, bd + 2u * k, accum | (uint32_t)(k > 0));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < nks) tc_mma_tf32(d_addr, alo + 2u * k, bd + 2u * k, 1u);
+                        tc_commit(&bars.b_empty[bs]);
+                    }
+                    accum = 1;
+                    if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                    mbar_wait(&bars.b_full[bs], b_ph);
+                    tc_fence_after();
+                    bd = bdesc0 + (uint32_t)bs * B_UNITS;
+                    if (leader) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < nks) tc_mma_tf32(d_addr, ahi + 2u * k, bd + 2u * k, 1u);
+                        tc_commit(&bars.b_empty[bs]);
+                        tc_commit(&bars.a_empty[as]);
+                    }
+                    if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                    if (++as == NA) { as = 0; a_ph ^= 1; }
+                }
+                if (leader) tc_commit(&bars.acc_full[j & 1u]);
+                ++j;
+            }
+        }
+    } else if (warp >= BUILD_WARP0 && warp < BUILD_WARP0 + BUILD_WARPS) {
+        // ================================ A builders ==================================
+        // Two groups of four warps; group g converts every other feature block of this CTA's stream into
+        // A-ring slot g.  A group's loads for its NEXT block are in flight while it waits for its slot and
+        // converts the current one: two block times (~3000 MMA cycles) of latency tolerance per load.
+        const int grp = (warp - BUILD_WARP0) >> 2;
+        const int t = (threadIdx.x - BUILD_WARP0 * 32) & (TM - 1);     // patch row inside the tile
+        const int vec = P.g.vec;
+        const bool use_tab = D <= FOFF_MAX;
+        // 32 features [32 fb, 32 fb + 32) of one patch row; zero beyond D and for padding rows
+        // whole-fmap patches (Seq = 1, D % 32 == 0): a patch row is one contiguous run, so the warp reads full
+        // 128-byte lines -- lane l takes chunk (l & 7) of rows wrow0 + 4 i + (l >> 3), i = 0..7 -- instead of
+        // every lane walking its own row
+        const bool contig = (P.g.seq == 1) && ((D & 31) == 0) && ((reinterpret_cast<uintptr_t>(P.x) & 15) == 0);
+        const int wrow0 = t & ~31;                                     // first row of this warp
+        int64_t m_rows0 = 0;                                           // first patch of the current job's tile
+        auto load_fb = [&](float (&v)[32], const float* src, bool ok, int fb) {
+            if (contig) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t pr = m_rows0 + wrow0 + 4 * i + (lane >> 3);
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pr < P.rows && !(P.dbg & 1))
+                        f = __ldg(reinterpret_cast<const float4*>(P.x + pr * D + fb * 32 + (lane & 7) * 4));
+                    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+                }
+                return;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int d = fb * 32 + c * 4;
+                float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+                if (ok && d < D && !(P.dbg & 1)) {
+                    if (vec == 4) {
+                        const int o = use_tab ? aux.foff[d] : feat_off(P.g, d);
+                        const float4 f = __ldg(reinterpret_cast<const float4*>(src + o));
+                        tmp[0] = f.x; tmp[1] = f.y; tmp[2] = f.z; tmp[3] = f.w;
+                    } else if (vec == 2) {
+                        const int o0 = use_tab ? aux.foff[d] : feat_off(P.g, d);
+                        const float2 f0 = __ldg(reinterpret_cast<const float2*>(src + o0));
+                        tmp[0] = f0.x; tmp[1] = f0.y;
+                        if (d + 2 < D) {
+                            const int o1 = use_tab ? aux.foff[d + 2] : feat_off(P.g, d + 2);
+                            const float2 f1 = __ldg(reinterpret_cast<const float2*>(src + o1));
+                            tmp[2] = f1.x; tmp[3] = f1.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (d + e < D) tmp[e] = __ldg(src + (use_tab ? aux.foff[d + e] : feat_off(P.g, d + e)));
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[c * 4 + e] = tmp[e];
+            }
+        };
+        // position in this CTA's (job, unit tile, feature block) stream
+        int q = blockIdx.x, n = 0, fb = 0, fb0 = 0, fb1 = 0;
+        bool ok = false, live = q < n_jobs;
+        const float* src = P.x;
+        auto enter_job = [&]() {
+            const int s = q % P.S, m = q / P.S;
+            fb0 = s * P.fb_per_split;
+            fb1 = min(P.DB, fb0 + P.fb_per_split);
+            fb = fb0;
+            n = 0;
+            const int64_t p = (int64_t)m * TM + t;
+            m_rows0 = (int64_t)m * TM;
+            ok = p < P.rows;
+            src = P.x + (ok ? patch_base(P.g, p) : 0);
+        };
+        auto advance = [&]() {
+            if (!live) return;
+            if (++fb == fb1) {
+                fb = fb0;
+                if (++n == P.NT) {
+                    q += gridDim.x;
+                    if (q >= n_jobs) { live = false; return; }
+                    enter_job();
+                }
+            }
+        };
+        if (live) enter_job();
+        if (grp == 1) advance();
+        uint32_t a_eph = 1;
+        float cur[32], nxt[32];
+        if (live) load_fb(cur, src, ok, fb);
+        while (live) {
+            advance();
+            advance();
+            const bool more = live;
+            if (more) load_fb(nxt, src, ok, fb);
+            mbar_wait_warp<false>(&bars.a_empty[grp], a_eph, lane);
+            uint8_t* hi_blk = a_ring + (size_t)grp * A_SLOT_BYTES;
+            uint8_t* lo_blk = hi_blk + A_BLK_BYTES;
+            if (!(P.dbg & 2))
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 hi, lo;
+                hi.x = tf32_rna(cur[4 * c]);     lo.x = tf32_rna(cur[4 * c] - hi.x);
+                hi.y = tf32_rna(cur[4 * c + 1]); lo.y = tf32_rna(cur[4 * c + 1] - hi.y);
+                hi.z = tf32_rna(cur[4 * c + 2]); lo.z = tf32_rna(cur[4 * c + 2] - hi.z);
+                hi.w = tf32_rna(cur[4 * c + 3]); lo.w = tf32_rna(cur[4 * c + 3] - hi.w);
+                // 16-byte chunk q of row r lives at r * 128 + ((q ^ (r & 7)) << 4)
+                const uint32_t r = contig ? (uint32_t)(wrow0 + 4 * c + (lane >> 3)) : (uint32_t)t;
+                const uint32_t qk = contig ? (uint32_t)(lane & 7) : (uint32_t)c;
+                const uint32_t off = r * 128u + ((qk ^ (r & 7u)) << 4);
+                *reinterpret_cast<float4*>(hi_blk + off) = hi;
+                *reinterpret_cast<float4*>(lo_blk + off) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.a_full[grp]);
+            a_eph ^= 1;
+            if (!more) break;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ================================ epilogue ====================================
+        // four warps, one per TMEM lane quarter; a thread owns one patch row and walks all 256 columns
+        const int lg = warp & 3;                    // TMEM lane quarter this warp may access
+        const int row = lg * 32 + lane;             // patch row inside the tile
+        uint32_t j = 0;
+        for (int q = blockIdx.x; q < n_jobs; q += gridDim.x) {
+            const int s = q % P.S, m = q / P.S;
+            const int64_t p = (int64_t)m * TM + row;
+            float best = INFINITY;
+            int bidx = 0;
+            for (int n = 0; n < P.NT; ++n) {
+                const uint32_t acc = j & 1u;
+                mbar_wait(&bars.acc_full[acc], (j >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TN;
+                const int col0 = n * TN;
+                uint32_t va[32], vb[32];
+                auto consume = [&](const uint32_t (&v)[32], int c) {
+                    if (SPLITK) {
+                        if (p < P.rows) {
+                            float4* dst = reinterpret_cast<float4*>(
+                                P.partial + ((int64_t)s * P.n_mtiles * TM + p) * P.K_pad + col0 + c * 32);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                        }
+                    } else {
+                        const float mn = min32(v);
+                        if (mn < best) { best = mn; bidx = col0 + c * 32 + first_eq32(v, mn); }
+                    }
+                };
+                tmem_ld32_issue(taddr, va);
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    tmem_ld_wait(va);
+                    tmem_ld32_issue(taddr + (c + 1) * 32, vb);
+                    consume(va, c);
+                    tmem_ld_wait(vb);
+                    if (c + 2 < 8) {
+                        tmem_ld32_issue(taddr + (c + 2) * 32, va);
+                    } else {
+                        // accumulator fully read: hand it back before the last reduction
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars.acc_empty[acc]);
+                    }
+                    consume(vb, c + 1);
+                }
+                ++j;
+            }
+            if (!SPLITK && p < P.rows) {
+                P.out_idx[p] = (int64_t)bidx + P.unit_offset;
+                if (P.out_rd) P.out_rd[p] = best;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// split-K tail: rd[p][j] = sum_s partial[s][p][j] in fixed order, then the argmin over the K real units
+// (ascending j per lane + strict '<', ties between lanes to the lower index: lowest index wins)
+__global__ void __launch_bounds__(256) splitk_argmin_kernel(const float* __restrict__ partial, int S, int64_t n_pad,
+                                                            int K_pad, int K, int64_t rows, int64_t unit_offset,
+                                                            int64_t* __restrict__ out_idx, float* __restrict__ out_rd) {
+    const int64_t p = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= rows) return;
+    float best = INFINITY;
+    int bidx = 0x7fffffff;
+    for (int j = lane; j < K; j += 32) {
+        float v = 0.f;
+        for (int s = 0; s < S; ++s) v += partial[((int64_t)s * n_pad + p) * K_pad + j];
+        if (v < best) { best = v; bidx = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (lane == 0) {
+        out_idx[p] = (int64_t)bidx + unit_offset;
+        if (out_rd) out_rd[p] = best;
+    }
+}
+
+// pre-split codebook: row j = [ -2 hi(c) for every 32-feature block | -2 lo(c) for every block ], zero beyond D;
+// tail rows [n1 n2 n3 0 0 0 0 0]; rows >= K are padding units whose norm can never be the minimum
+__global__ void __launch_bounds__(256) split_w_l_kernel(const float* __restrict__ W, const float* __restrict__ cn,
+                                                        int K, int D, int DB, int K_pad, float* __restrict__ Bp,
+                                                        float* __restrict__ Tp) {
+    const int64_t cols = (int64_t)DB * 32;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)K_pad * cols) return;
+    const int row = (int)(t / cols);
+    const int d = (int)(t - (int64_t)row * cols);
+    float hi = 0.f, lo = 0.f;
+    if (row < K && d < D) {
+        const float w = W[(int64_t)row * D + d];
+        const float h = tf32_rna(w);
+        hi = -2.0f * h;
+        lo = -2.0f * tf32_rna(w - h);
+    }
+    Bp[(int64_t)row * 2 * cols + d] = hi;
+    Bp[(int64_t)row * 2 * cols + cols + d] = lo;
+    if (d < 8) {
+        float out = 0.f;
+        if (row < K) {
+            const float nrm = cn[row];
+            const float n1 = tf32_rna(nrm);
+            const float n2 = tf32_rna(nrm - n1);
+            const float n3 = tf32_rna(nrm - n1 - n2);
+            out = (d == 0) ? n1 : (d == 1) ? n2 : (d == 2) ? n3 : 0.f;
+        } else if (d == 0) {
+            out = PAD_NORM;
+        }
+        Tp[(int64_t)row * 8 + d] = out;
+    }
+}
+
+struct Plan {
+    int D, K, DB, nks_last, K_pad, NT, n_mtiles, S, fb_per_split;
+    size_t off_b, off_t, off_p, total;
+};
+
+static void make_plan(Plan* pl, int64_t n, int D, int K) {
+    pl->D = D; pl->K = K;
+    pl->DB = (D + 31) / 32;
+    pl->nks_last = (D - 32 * (pl->DB - 1) + 7) / 8;
+    pl->K_pad = (K + TN - 1) / TN * TN;
+    pl->NT = pl->K_pad / TN;
+    pl->n_mtiles = (int)ceil_div64(n, TM);
+    // static split rule: with fewer patch tiles than SMs, cut the feature axis so that every SM gets a job,
+    // but keep at least 8 blocks (~12k MMA cycles) per split
+    int S = sm_count() / pl->n_mtiles;
+    if (S > pl->DB / 8) S = pl->DB / 8;
+    if (S > MAX_SPLIT) S = MAX_SPLIT;
+    if (S < 1) S = 1;
+    pl->fb_per_split = (pl->DB + S - 1) / S;
+    pl->S = (pl->DB + pl->fb_per_split - 1) / pl->fb_per_split;
+    size_t o = 0;
+    pl->off_b = o; o = align_up(o + (size_t)pl->K_pad * pl->DB * 64 * 4, 1024);
+    pl->off_t = o; o = align_up(o + (size_t)pl->K_pad * 8 * 4, 1024);
+    pl->off_p = o;
+    if (pl->S > 1) o = align_up(o + (size_t)pl->S * pl->n_mtiles * TM * pl->K_pad * 4, 1024);
+    pl->total = o;
+}
+
+}  // namespace tcl
+
+// static rule: the fused-builder kernel is the split-K path (few patch tiles, long feature axis); with enough
+// patch tiles to fill the machine the TMA-fed path of som_bmu_tc.cu is faster (measured at config 5:
+// 80.7 ms vs 96 ms), so it keeps those shapes
+int tc_l_splits(int64_t n_patches, int D, int K) {
+    tcl::Plan pl;
+    tcl::make_plan(&pl, n_patches, D, K);
+    return pl.S;
+}
+
+size_t tc_l_workspace_bytes(int64_t n_patches, int D, int K) {
+    tcl::Plan pl;
+    tcl::make_plan(&pl, n_patches, D, K);
+    return pl.total;
+}
+
+int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
+                    int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, cudaStream_t st) {
+    using namespace tcl;
+    const int64_t n = g.n_patches;
+    if (n == 0) return SOM_OK;
+    Plan pl;
+    make_plan(&pl, n, g.D, K);
+    SOM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, SOM_E_WORKSPACE, "bmu(tc): workspace %zu < required %zu",
+                ws_bytes, pl.total);
+    SOM_REQUIRE(((uintptr_t)ws & 255) == 0, SOM_E_BADARG, "bmu(tc): workspace must be 256-byte aligned");
+    float* Bp = (float*)((char*)ws + pl.off_b);
+    float* Tp = (float*)((char*)ws + pl.off_t);
+    float* Pp = (float*)((char*)ws + pl.off_p);
+    {
+        const int64_t items = (int64_t)pl.K_pad * pl.DB * 32;
+        split_w_l_kernel<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(W, cn, K, g.D, pl.DB, pl.K_pad, Bp, Tp);
+        int rc = check_launch("split_w_l_kernel");
+        if (rc) return rc;
+    }
+    CUtensorMap map_b, map_t;
+    int rc = make_map2d(&map_b, Bp, (uint64_t)pl.K_pad, (uint64_t)pl.DB * 64, (uint64_t)pl.DB * 64 * 4, 32, TN,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map2d(&map_t, Tp, (uint64_t)pl.K_pad, 8, 32, 8, TN, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+
+    Params P;
+    P.DB = pl.DB; P.nks_last = pl.nks_last; P.NT = pl.NT; P.n_mtiles = pl.n_mtiles; P.S = pl.S;
+    P.fb_per_split = pl.fb_per_split; P.K_pad = pl.K_pad; P.rows = n; P.unit_offset = unit_offset;
+    P.out_idx = out_idx; P.out_rd = out_rd; P.partial = pl.S > 1 ? Pp : nullptr; P.x = x; P.g = g;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SOM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(bmu_tc_l_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(bmu_tc_l_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_done = true;
+    }
+    const int n_jobs = pl.n_mtiles * pl.S;
+    const int grid = n_jobs < sm_count() ? n_jobs : sm_count();
+    if (pl.S > 1) {
+        bmu_tc_l_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
+        rc = check_launch("bmu_tc_l_kernel<splitk>");
+        if (rc) return rc;
+        splitk_argmin_kernel<<<(unsigned)ceil_div64(n, 8), 256, 0, st>>>(Pp, pl.S, (int64_t)pl.n_mtiles * TM, pl.K_pad, K,
+                                                                       n, unit_offset, out_idx, out_rd);
+        return check_launch("splitk_argmin_kernel");
+    }
+    bmu_tc_l_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
+    return check_launch("bmu_tc_l_kernel");
+}
+
+}  // namespace som
