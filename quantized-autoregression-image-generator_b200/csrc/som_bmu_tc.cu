@@ -662,8 +662,10 @@ int tc_l_splits(int64_t n_patches, int D, int K);
 static bool use_l2(int64_t n_patches, int D, int K) {
     static int mode = -1;           // SOM_TC_L=0: never, 2: always (A/B comparisons only); default: split-K shapes
     if (mode < 0) { const char* e = getenv("SOM_TC_L"); mode = e ? atoi(e) : 1; }
+    if (mode == 0) return false;
+    if (D <= 64) return true;       // resident-A mode of the fused-builder kernel (config M, D in 17..64)
     const int kb = (3 * D + 3 + tc::KBLK - 1) / tc::KBLK;
-    if (mode == 0 || (kb <= 7 && D <= tc::DCAP_M)) return false;
+    if (kb <= 7 && D <= tc::DCAP_M) return false;
     return mode == 2 || tc_l_splits(n_patches, D, K) > 1;
 }
 static bool use_s4(int D) {

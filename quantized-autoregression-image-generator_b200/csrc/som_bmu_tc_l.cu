@@ -85,7 +85,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
            (6ull << 61);
 }
 
-template <bool SPLITK>
+// SPLITK: partial-distance epilogue (feature axis split over CTAs).  ARES: the patch tile's operand blocks stay
+// resident in the two A slots for all unit tiles (D <= 64: one slot per 32-feature block) instead of streaming.
+template <bool SPLITK, bool ARES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
     extern __shared__ uint8_t smem_raw[];
@@ -174,6 +176,7 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         int as = 0, bs = 0, ts = 0;
         uint32_t a_ph = 0, b_ph = 0, t_ph = 0, j = 0;
         for (int q = blockIdx.x; q < n_jobs; q += gridDim.x) {
+            if (ARES && q != (int)blockIdx.x) a_ph ^= 1;           // resident slots: one fill per job
             const int s = q % P.S;
             const int fb0 = s * P.fb_per_split;
             const int fb1 = min(P.DB, fb0 + P.fb_per_split);
@@ -194,9 +197,10 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 }
                 for (int fb = fb0; fb < fb1; ++fb) {
                     const int nks = (fb == P.DB - 1) ? P.nks_last : 4;
+                    if (ARES) as = fb;
                     const uint64_t ahi = adesc0 + (uint32_t)as * A_SLOT_UNITS;
                     const uint64_t alo = ahi + A_LO_UNITS;
-                    mbar_wait(&bars.a_full[as], a_ph);
+                    if (!ARES || n == 0) mbar_wait(&bars.a_full[as], a_ph);
                     mbar_wait(&bars.b_full[bs], b_ph);
                     tc_fence_after();
                     uint64_t bd = bdesc0 + (uint32_t)bs * B_UNITS;
@@ -219,10 +223,10 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                         for (int k = 0; k < 4; ++k)
                             if (k < nks) tc_mma_tf32(d_addr, ahi + 2u * k, bd + 2u * k, 1u);
                         tc_commit(&bars.b_empty[bs]);
-                        tc_commit(&bars.a_empty[as]);
+                        if (!ARES || n == P.NT - 1) tc_commit(&bars.a_empty[as]);
                     }
                     if (++bs == NB) { bs = 0; b_ph ^= 1; }
-                    if (++as == NA) { as = 0; a_ph ^= 1; }
+                    if (!ARES && ++as == NA) { as = 0; a_ph ^= 1; }
                 }
                 if (leader) tc_commit(&bars.acc_full[j & 1u]);
                 ++j;
@@ -301,6 +305,13 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         };
         auto advance = [&]() {
             if (!live) return;
+            if (ARES) {                       // resident mode: this group's block of the next job
+                q += gridDim.x;
+                if (q >= n_jobs) { live = false; return; }
+                enter_job();
+                fb = grp;
+                return;
+            }
             if (++fb == fb1) {
                 fb = fb0;
                 if (++n == P.NT) {
@@ -311,13 +322,18 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             }
         };
         if (live) enter_job();
-        if (grp == 1) advance();
+        if (ARES) {
+            fb = grp;
+            if (grp >= P.DB) live = false;
+        } else if (grp == 1) {
+            advance();
+        }
         uint32_t a_eph = 1;
         float cur[32], nxt[32];
         if (live) load_fb(cur, src, ok, fb);
         while (live) {
             advance();
-            advance();
+            if (!ARES) advance();
             const bool more = live;
             if (more) load_fb(nxt, src, ok, fb);
             mbar_wait_warp<false>(&bars.a_empty[grp], a_eph, lane);
@@ -552,24 +568,30 @@ int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* 
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SOM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(bmu_tc_l_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(bmu_tc_l_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(bmu_tc_l_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+            e = cudaFuncSetAttribute(bmu_tc_l_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(bmu_tc_l_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
     const int n_jobs = pl.n_mtiles * pl.S;
     const int grid = n_jobs < sm_count() ? n_jobs : sm_count();
     if (pl.S > 1) {
-        bmu_tc_l_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
+        bmu_tc_l_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
         rc = check_launch("bmu_tc_l_kernel<splitk>");
         if (rc) return rc;
         splitk_argmin_kernel<<<(unsigned)ceil_div64(n, 8), 256, 0, st>>>(Pp, pl.S, (int64_t)pl.n_mtiles * TM, pl.K_pad, K,
                                                                        n, unit_offset, out_idx, out_rd);
         return check_launch("splitk_argmin_kernel");
     }
-    bmu_tc_l_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
+    if (pl.DB <= NA) {
+        bmu_tc_l_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
+        return check_launch("bmu_tc_l_kernel<resident>");
+    }
+    bmu_tc_l_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
     return check_launch("bmu_tc_l_kernel");
 }
 
