@@ -126,6 +126,18 @@ SOM_API int som_adam_f32(float* W, float* m, float* v, const float* g, int64_t n
 SOM_API int som_gather_rows_f32(const float* W, int D, const int64_t* keep, int64_t n_keep,
                         float* out, void* stream);
 
+/* ---- dual-codebook token assembly (tokenisation call site of the Transformer trainer) ----
+ * Replaces the index arithmetic of train_quantized_transformer.py:411-455 after the two
+ * get_patches_bmu calls: lr_idx (n, lr_seq) and hr_idx (n, hr_seq) are the UNSHIFTED BMU
+ * indices of the low- / high-resolution codebooks of the same feature maps.
+ *   base_model != 0 : hr_input (n, lr_seq + hr_seq) = [ lr_idx | hr_idx + lr_K ]   (:425-431)
+ *   base_model == 0 : hr_input (n, 1 + hr_seq)      = [ hr_K   | hr_idx ]          (:436-441)
+ *   always          : hr_target (n, hr_seq + 1)     = [ hr_idx | hr_K ]            (:449-454)
+ * hr_K (= hr_num_embeddings) is the reference's <start>/<end> token.                       */
+SOM_API int som_assemble_tokens_i64(const int64_t* lr_idx, const int64_t* hr_idx, int64_t n,
+                            int lr_seq, int hr_seq, int64_t lr_K, int64_t hr_K, int base_model,
+                            int64_t* hr_input, int64_t* hr_target, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

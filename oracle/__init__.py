@@ -29,3 +29,4 @@ from .step_oracle import (  # noqa: F401
     synthetic_fmaps,
     trained_like_codebook,
 )
+from .tokens_oracle import tokenize_pair_oracle  # noqa: F401

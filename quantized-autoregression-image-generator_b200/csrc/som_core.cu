@@ -138,6 +138,35 @@ __global__ void __launch_bounds__(256) hist_global_kernel(const int64_t* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// token assembly for the Transformer trainer (train_quantized_transformer.py:411-455): one pass writes
+// hr_input and hr_target from the two BMU index tensors -- replaces add / cat / repeat / cat
+// one thread per output element; a row of hr_input followed by the row of hr_target
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const int64_t* __restrict__ lr_idx,
+                                                              const int64_t* __restrict__ hr_idx, int64_t n,
+                                                              int lr_seq, int hr_seq, int64_t lr_K, int64_t hr_K,
+                                                              int base_model, int64_t* __restrict__ hr_input,
+                                                              int64_t* __restrict__ hr_target) {
+    const int in_w = base_model ? lr_seq + hr_seq : 1 + hr_seq;
+    const int row_w = in_w + hr_seq + 1;
+    const int64_t total = n * (int64_t)row_w;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t / row_w;
+        const int c = (int)(t - i * row_w);
+        if (c < in_w) {
+            int64_t v;
+            if (base_model) v = (c < lr_seq) ? lr_idx[i * lr_seq + c] : hr_idx[i * hr_seq + (c - lr_seq)] + lr_K;
+            else v = (c == 0) ? hr_K : hr_idx[i * hr_seq + (c - 1)];
+            hr_input[i * in_w + c] = v;
+        } else {
+            const int k = c - in_w;
+            hr_target[i * (int64_t)(hr_seq + 1) + k] = (k < hr_seq) ? hr_idx[i * hr_seq + k] : hr_K;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // quantise: out[offset(p, d)] = table[idx[p]][d]   (gather + fused unpatchify)
 // one thread per VEC-wide run; consecutive threads walk d fastest inside a patch
 // ---------------------------------------------------------------------------------------------
@@ -280,6 +309,22 @@ int som_quantize_nchw_f32(const int64_t* idx, const float* table, int K,
     else if (vec == 2) quantize_kernel<2><<<blocks, 256, 0, s>>>(idx, table, K, g, out);
     else quantize_kernel<1><<<blocks, 256, 0, s>>>(idx, table, K, g, out);
     return check_launch("quantize_kernel");
+}
+
+int som_assemble_tokens_i64(const int64_t* lr_idx, const int64_t* hr_idx, int64_t n, int lr_seq, int hr_seq,
+                            int64_t lr_K, int64_t hr_K, int base_model, int64_t* hr_input, int64_t* hr_target,
+                            void* stream) {
+    SOM_REQUIRE(hr_idx && hr_input && hr_target, SOM_E_BADARG, "assemble_tokens: null pointer");
+    SOM_REQUIRE(!base_model || lr_idx, SOM_E_BADARG, "assemble_tokens: base model needs lr_idx");
+    SOM_REQUIRE(n >= 0 && hr_seq > 0 && lr_seq >= 0, SOM_E_BADARG, "assemble_tokens: n=%lld lr_seq=%d hr_seq=%d",
+                (long long)n, lr_seq, hr_seq);
+    if (n == 0) return SOM_OK;
+    const int in_w = base_model ? lr_seq + hr_seq : 1 + hr_seq;
+    const int64_t items = n * (int64_t)(in_w + hr_seq + 1);
+    int blocks = grid_for(items, 256, 16);
+    assemble_tokens_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(lr_idx, hr_idx, n, lr_seq, hr_seq, lr_K, hr_K,
+                                                                     base_model, hr_input, hr_target);
+    return check_launch("assemble_tokens_kernel");
 }
 
 int som_adam_f32(float* W, float* m, float* v, const float* g, int64_t n,

@@ -13,6 +13,7 @@ from .trainer import SomTrainer, prune_codebook, bmu_histogram  # noqa: E402,F40
 from .distributed import (  # noqa: E402,F401
     DataParallelSom, sharded_bmu, shard_bounds, split_batch)
 from .host_pipeline import HostTokenizer  # noqa: E402,F401
+from .tokenizer import tokenize_pair  # noqa: E402,F401
 
 __all__ = ["Codebook", "patchify", "unpatchify", "SomTrainer", "prune_codebook", "bmu_histogram",
-           "DataParallelSom", "sharded_bmu", "shard_bounds", "split_batch", "HostTokenizer", "ops"]
+           "DataParallelSom", "sharded_bmu", "shard_bounds", "split_batch", "HostTokenizer", "tokenize_pair", "ops"]

@@ -218,3 +218,27 @@ def gather_rows(weight, keep):
         check("som_gather_rows_f32",
               lib.som_gather_rows_f32(_ptr(w), w.shape[1], _ptr(keep), keep.numel(), _ptr(out), _stream(w)))
     return out
+
+
+def assemble_tokens(lr_idx, hr_idx, lr_num_embeddings, hr_num_embeddings, base_model):
+    """Token tensors of train_quantized_transformer.py:411-455 from the two (n, Seq) BMU index
+    tensors in one launch.  Returns (hr_input, hr_target)."""
+    lib = _lib.load()
+    hr_idx = _req(hr_idx, torch.int64, "hr_idx")
+    n, hr_seq = hr_idx.shape
+    lr_seq = 0
+    if lr_idx is not None:
+        lr_idx = _req(lr_idx, torch.int64, "lr_idx")
+        if lr_idx.shape[0] != n:
+            raise ValueError("lr_idx and hr_idx disagree on the batch size")
+        lr_seq = lr_idx.shape[1]
+    in_w = lr_seq + hr_seq if base_model else 1 + hr_seq
+    hr_input = torch.empty(n, in_w, dtype=torch.int64, device=hr_idx.device)
+    hr_target = torch.empty(n, hr_seq + 1, dtype=torch.int64, device=hr_idx.device)
+    with torch.cuda.device(hr_idx.device):
+        check("som_assemble_tokens_i64",
+              lib.som_assemble_tokens_i64(_ptr(lr_idx), _ptr(hr_idx), n, lr_seq, hr_seq,
+                                          int(lr_num_embeddings), int(hr_num_embeddings),
+                                          1 if base_model else 0, _ptr(hr_input), _ptr(hr_target),
+                                          _stream(hr_idx)))
+    return hr_input, hr_target

@@ -152,3 +152,32 @@ def test_reference_tokenisation_call_sequence():
         assert img.shape == x.shape
         assert torch.equal(cb.get_patches_bmu(img, reshape=True), idx), "codec round trip"
     assert outs[0].shape == (8, 64) and outs[1].shape == (8, 256)
+
+
+@pytest.mark.parametrize("base_model", [True, False])
+def test_tokenize_pair_matches_reference_call_sequence(base_model):
+    """train_quantized_transformer.py:411-455 on the drop-in modules: both BMU searches and the
+    fused token assembly against the CPU restatement, bit-exact."""
+    from oracle import tokenize_pair_oracle
+    from oracle.step_oracle import make_oracle_codebook
+    x = synthetic_fmaps(24, 77)
+    specs = [((8, 8), 300), ((2, 2), 1000)]               # low-res / high-res codebooks
+    ocs, gcs = [], []
+    for pd, k in specs:
+        w = trained_like_codebook(k, pd, 21 + k)
+        ocs.append(make_oracle_codebook(w, pd, (32, 32), 4, k // 2))
+        cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                            init_neighbour_range=k // 2)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(w)
+        gcs.append(cb.to(DEV).eval())
+    ref_in, ref_tgt, ref_lr = tokenize_pair_oracle(ocs[0], ocs[1], x, base_model)
+    got_in, got_tgt, got_lr = somcb.tokenize_pair(gcs[0], gcs[1], x.to(DEV), base_model)
+    assert got_in.dtype == torch.int64 and got_in.shape == ref_in.shape
+    assert torch.equal(got_in.cpu(), ref_in) and torch.equal(got_tgt.cpu(), ref_tgt)
+    if base_model:
+        assert got_lr is None and ref_lr is None
+        assert int(got_in[:, :16].max()) < 300 and int(got_in[:, 16:].min()) >= 300
+    else:
+        assert torch.equal(got_lr.cpu(), ref_lr) and int(got_in[:, 0].min()) == 1000
+    assert int(got_tgt[:, -1].min()) == 1000 and int(got_tgt[:, -1].max()) == 1000

@@ -114,3 +114,19 @@ def test_band_half_width_values():
     assert oracle.band_half_width(512) == 152
     assert oracle.band_half_width(8192) == 608
     assert oracle.band_half_width(1) == 6
+
+
+def test_token_assembly_oracle_shapes_and_tokens():
+    """The tokeniser restatement (train_quantized_transformer.py:411-455): shapes, shift, <start>/<end>."""
+    from oracle import tokenize_pair_oracle
+    from oracle.step_oracle import make_oracle_codebook, synthetic_fmaps, trained_like_codebook
+    x = synthetic_fmaps(3, 5)
+    lr = make_oracle_codebook(trained_like_codebook(50, (8, 8), 1), (8, 8), (32, 32), 4, 25)
+    hr = make_oracle_codebook(trained_like_codebook(70, (4, 4), 2), (4, 4), (32, 32), 4, 35)
+    hi, ht, li = tokenize_pair_oracle(lr, hr, x, True)
+    assert hi.shape == (3, 16 + 64) and ht.shape == (3, 65) and li is None
+    assert int(hi[:, :16].max()) < 50 and int(hi[:, 16:].min()) >= 50 and bool((ht[:, -1] == 70).all())
+    assert torch.equal(hi[:, 16:] - 50, ht[:, :-1])
+    hi2, ht2, li2 = tokenize_pair_oracle(lr, hr, x, False)
+    assert hi2.shape == (3, 65) and bool((hi2[:, 0] == 70).all()) and torch.equal(hi2[:, 1:], ht2[:, :-1])
+    assert torch.equal(li2, hi[:, :16]) and torch.equal(ht, ht2)
