@@ -14,6 +14,8 @@ from .distributed import (  # noqa: E402,F401
     DataParallelSom, sharded_bmu, shard_bounds, split_batch)
 from .host_pipeline import HostTokenizer  # noqa: E402,F401
 from .tokenizer import tokenize_pair  # noqa: E402,F401
+from . import fmap_shards  # noqa: E402,F401
+from .fmap_shards import ShardReader, convert_reference_dataset  # noqa: E402,F401
 
 __all__ = ["Codebook", "patchify", "unpatchify", "SomTrainer", "prune_codebook", "bmu_histogram",
-           "DataParallelSom", "sharded_bmu", "shard_bounds", "split_batch", "HostTokenizer", "tokenize_pair", "ops"]
+           "DataParallelSom", "sharded_bmu", "shard_bounds", "split_batch", "HostTokenizer", "tokenize_pair", "ShardReader", "convert_reference_dataset", "ops"]

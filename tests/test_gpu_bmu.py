@@ -196,3 +196,21 @@ def test_tensor_core_ties_inside_and_across_chunks():
         idx = cb.get_patches_bmu(x.to(DEV)).cpu()
         assert int(idx.max()) < 300, f"variant {variant}: a later duplicate won"
         assert_bmu_parity(idx, ref, flat_patches(x, pd), w)
+
+
+@pytest.mark.parametrize("env", [{"SOM_TC_L": "2"}, {"SOM_TC_L": "0"}, {"SOM_TC_OLD_S": "1"}])
+def test_alternate_tensor_core_paths_in_a_subprocess(env):
+    """The static dispatch keeps some tensor-core kernels for specific shapes only (fused-builder kernel
+    in ARGMIN streaming mode, the TMA-fed configs M / L, the previous config S).  The override switches
+    are read once per process, so each alternative runs the parity probe in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = os.path.join(root, "tools", "tc_probe.py")
+    shapes = [("16", "8", "2048"), ("40", "4", "1000"), ("3", "8", "777"), ("64", "2", "4093")]
+    for shp in shapes:
+        r = subprocess.run([sys.executable, probe, *shp, "2"], env={**os.environ, **env},
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, f"{env} {shp}: {r.stdout[-400:]} {r.stderr[-800:]}"
+        assert "OK:" in r.stdout, r.stdout[-400:]

@@ -181,3 +181,27 @@ def test_tokenize_pair_matches_reference_call_sequence(base_model):
     else:
         assert torch.equal(got_lr.cpu(), ref_lr) and int(got_in[:, 0].min()) == 1000
     assert int(got_tgt[:, -1].min()) == 1000 and int(got_tgt[:, -1].max()) == 1000
+
+
+def test_shard_reader_feeds_host_tokenizer(tmp_path):
+    """Packed shards -> pinned batches -> HostTokenizer == one resident-batch BMU call."""
+    from somcb import fmap_shards as fs
+    x = synthetic_fmaps(300, 31)
+    fs.write_shard(str(tmp_path / "a.shard"), x[:180].numpy())
+    fs.write_shard(str(tmp_path / "b.shard"), x[180:].numpy())
+    reader = fs.ShardReader([str(tmp_path / "a.shard"), str(tmp_path / "b.shard")], batch_fmaps=64)
+    pd, k = (2, 2), 777
+    cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                        init_neighbour_range=k // 2)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(trained_like_codebook(k, pd, 5))
+    cb = cb.to(DEV).eval()
+    tok = somcb.HostTokenizer(cb, chunk_fmaps=48, depth=3)
+    ref = cb.get_patches_bmu(x.to(DEV), reshape=True).cpu()
+    counts = None
+    for lo, hi, batch in reader.batches():
+        idx = tok.tokenize(batch)
+        torch.cuda.synchronize()
+        assert torch.equal(idx, ref[lo:hi])
+        counts = ops.histogram(idx.to(DEV).reshape(-1), k, counts)
+    assert torch.equal(counts.cpu(), torch.bincount(ref.reshape(-1), minlength=k))

@@ -135,3 +135,47 @@ def test_trainer_schedule_bookkeeping():
     assert set(ck) == {"patch_dim", "image_dim", "image_C", "num_embeddings", "neighbourhood_range",
                        "global_steps", "checkpoint"}
     assert ck["global_steps"] == 8 and list(ck["checkpoint"]) == ["codebook.weight"]
+
+
+def test_fmap_shards_round_trip_from_reference_layout(tmp_path):
+    """The reference's on-disk dataset (generate_fmap_dataset.py:42-72: one .npy per fmap, <=1000 per
+    folder, TinyDB json) -> packed shards -> ShardReader batches: values, order and image paths."""
+    import json
+    import numpy as np
+    import torch
+    from somcb import fmap_shards as fs
+    rng = np.random.default_rng(3)
+    src = tmp_path / "ref"
+    docs, maps = {}, []
+    for i in range(37):
+        folder = src / str(i // 10)                       # the reference's folder roll-over
+        folder.mkdir(parents=True, exist_ok=True)
+        fmap = np.tanh(rng.standard_normal((4, 8, 8))).astype(np.float32)
+        path = folder / str(i)
+        with open(path, "wb") as f:
+            np.save(f, fmap, allow_pickle=False)
+        maps.append(fmap)
+        docs[str(i + 1)] = {"fmap_path": str(path), "image_path": f"img_{i}.jpg"}
+    db = src / "all_dataset.json"
+    db.write_text(json.dumps({"_default": docs}))
+    shards = fs.convert_reference_dataset(str(db), str(tmp_path / "packed"), fmaps_per_shard=16)
+    assert len(shards) == 3 and [fs.read_header(s)[3] for s in shards] == [16, 16, 5]
+    reader = fs.ShardReader(shards, batch_fmaps=7, pin=False)
+    assert len(reader) == 37 and reader.shape == (4, 8, 8)
+    ref = torch.from_numpy(np.stack(maps))
+    assert torch.equal(reader.read_all(), ref)
+    seen = 0
+    for lo, hi, t in reader.batches():
+        assert lo == seen and torch.equal(t, ref[lo:hi]) and t.dtype == torch.float32
+        seen = hi
+    assert seen == 37
+    idx = json.loads((tmp_path / "packed" / "index.json").read_text())
+    assert idx["entries"][20] == {"i": 20, "shard": 1, "row": 4, "image_path": "img_20.jpg"}
+    import pytest
+    (tmp_path / "empty.json").write_text(json.dumps({"_default": {}}))
+    with pytest.raises(Exception, match="No data found"):
+        fs.reference_entries(str(tmp_path / "empty.json"))
+    bad = tmp_path / "bad.shard"
+    bad.write_bytes(b"x" * 100)
+    with pytest.raises(ValueError):
+        fs.read_header(str(bad))
