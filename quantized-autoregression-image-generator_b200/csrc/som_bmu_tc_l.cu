@@ -38,7 +38,7 @@ namespace tcl {
 using namespace tc;
 
 constexpr int NA = 2;                        // A ring slots (hi + lo block)
-constexpr int NB = 4;                        // B ring stages (one 32 KB block)
+constexpr int B_RING_BYTES = 4 * B_BLK_BYTES;                   // 128 KB: 4 stages of 32 KB, or 8 of 16 KB per CTA of a pair
 constexpr int BUILD_WARP0 = 2, BUILD_WARPS = 8;             // two groups of 4 warps, alternate feature blocks
 constexpr int EPI_WARP0 = 10, EPI_WARPS = 4;
 constexpr int NUM_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;       // 448
@@ -47,7 +47,8 @@ constexpr int TAIL_A_BYTES = TM * 32;        // 4 KB
 constexpr int TAIL_B_BYTES = TN * 32;        // 8 KB
 constexpr int FOFF_MAX = 1024;               // feature-offset table entries kept in shared memory
 constexpr int MAX_SPLIT = 8;
-constexpr int TILES_BYTES = NA * A_SLOT_BYTES + NB * B_BLK_BYTES + TAIL_A_BYTES + 2 * TAIL_B_BYTES;   // 212 KB
+constexpr int NB_MAX = 8;
+constexpr int TILES_BYTES = NA * A_SLOT_BYTES + B_RING_BYTES + TAIL_A_BYTES + 2 * TAIL_B_BYTES;   // 212 KB
 
 struct Params {
     int DB;                 // 32-feature blocks
@@ -65,10 +66,12 @@ struct Params {
     const float* x;
     Geom g;
     int dbg;                // SOM_TC_DEBUG (timing experiments only)
+    int a_tma;              // streamed mode: A blocks arrive by TMA from the pre-split workspace (builders idle)
+    int tile0;              // first patch tile of this launch inside the workspace chunk numbering (0)
 };
 
 struct __align__(8) Barriers {
-    uint64_t b_full[NB], b_empty[NB];
+    uint64_t b_full[NB_MAX], b_empty[NB_MAX];
     uint64_t t_full[2], t_empty[2];
     uint64_t a_full[NA], a_empty[NA];
     uint64_t acc_full[2], acc_empty[2];
@@ -87,15 +90,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
 
 // SPLITK: partial-distance epilogue (feature axis split over CTAs).  ARES: the patch tile's operand blocks stay
 // resident in the two A slots for all unit tiles (D <= 64: one slot per 32-feature block) instead of streaming.
-template <bool SPLITK, bool ARES>
+// CG = 2: CTA pairs (cluster of two, cta_group::2).  Each CTA builds its own 128-patch A tile and loads HALF of
+// every B block (128 units); the leader CTA issues M256 x N256 MMAs that read both CTAs' shared memory, so B
+// costs each SM half the L2 traffic and half the shared-memory fill / operand-read bandwidth.
+template <bool SPLITK, bool ARES, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
+bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t,
+                const __grid_constant__ CUtensorMap map_a, const Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int B_STAGE = B_BLK_BYTES / CG;       // this CTA's share of a 256-unit block
+    constexpr int NB = B_RING_BYTES / B_STAGE;
+    constexpr int T_STAGE = TAIL_B_BYTES / CG;
     uint8_t* a_ring = tiles;
     uint8_t* b_ring = a_ring + NA * A_SLOT_BYTES;
-    uint8_t* a_tail = b_ring + NB * B_BLK_BYTES;
+    uint8_t* a_tail = b_ring + B_RING_BYTES;
     uint8_t* t_ring = a_tail + TAIL_A_BYTES;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int job0 = (CG == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int job_stride = (CG == 2) ? (int)cluster_count_x() : (int)gridDim.x;
     Aux& aux = *reinterpret_cast<Aux*>(t_ring + 2 * TAIL_B_BYTES);
     Barriers& bars = aux.bars;
 
@@ -106,8 +119,8 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < NB; ++s) { mbar_init(&bars.b_full[s], 1); mbar_init(&bars.b_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&bars.t_full[s], 1); mbar_init(&bars.t_empty[s], 1); }
-        for (int s = 0; s < NA; ++s) { mbar_init(&bars.a_full[s], BUILD_WARPS / 2); mbar_init(&bars.a_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&bars.acc_full[a], 1); mbar_init(&bars.acc_empty[a], EPI_WARPS); }
+        for (int s = 0; s < NA; ++s) { mbar_init(&bars.a_full[s], P.a_tma ? 1 : BUILD_WARPS / 2 * CG); mbar_init(&bars.a_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars.acc_full[a], 1); mbar_init(&bars.acc_empty[a], EPI_WARPS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (D <= FOFF_MAX)
@@ -121,76 +134,113 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         rowp[sw ^ 1u] = make_float4(0.f, 0.f, 0.f, 0.f);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (CG == 2) {                      // barriers of both CTAs initialised before anything arrives remotely
+        __syncthreads();
+        cluster_sync_all();
+    }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
-                     "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                         "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                         "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
-    const int n_jobs = P.n_mtiles * P.S;
+    // a job = (patch tile [pair], feature split); CTA `rank` of a pair owns patch tile CG * (q / S) + rank
+    const int n_jobs = ((P.n_mtiles + CG - 1) / CG) * P.S;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int bs = 0, ts = 0;
             uint32_t b_ph = 0, t_ph = 0;
-            for (int q = blockIdx.x; q < n_jobs; q += gridDim.x) {
+            // pair mode: both CTAs load their 128-unit half; only the leader arms its barrier, for both halves
+            const int row_off = (int)rank * (TN / CG);
+            int as = 0;
+            uint32_t a_eph = 1;
+            for (int q = job0; q < n_jobs; q += job_stride) {
                 const int s = q % P.S;
                 const int fb0 = s * P.fb_per_split;
                 const int fb1 = min(P.DB, fb0 + P.fb_per_split);
                 for (int n = 0; n < P.NT; ++n) {
                     if (s == 0) {
                         mbar_wait(&bars.t_empty[ts], t_ph ^ 1);
-                        mbar_expect_tx(&bars.t_full[ts], TAIL_B_BYTES);
-                        tma_load_2d(&map_t, &bars.t_full[ts], t_ring + ts * TAIL_B_BYTES, 0, n * TN);
+                        if (rank == 0) mbar_expect_tx(&bars.t_full[ts], TAIL_B_BYTES);
+                        if (CG == 1) tma_load_2d(&map_t, &bars.t_full[ts], t_ring + ts * T_STAGE, 0, n * TN);
+                        else tma_load_2d_pair(&map_t, &bars.t_full[ts], t_ring + ts * T_STAGE, 0, n * TN + row_off);
                         if (++ts == 2) { ts = 0; t_ph ^= 1; }
                     }
                     for (int fb = fb0; fb < fb1; ++fb) {
+                        if (P.a_tma) {
+                            // pre-split patch rows: hi and lo block of this CTA's tile into A slot `as`
+                            const int m = CG * (q / P.S) + (int)rank;
+                            mbar_wait(&bars.a_empty[as], a_eph);
+                            if (rank == 0) mbar_expect_tx(&bars.a_full[as], A_SLOT_BYTES * CG);
+                            uint8_t* adst = a_ring + (size_t)as * A_SLOT_BYTES;
+#pragma unroll
+                            for (int part = 0; part < 2; ++part) {
+                                if (CG == 1) tma_load_2d(&map_a, &bars.a_full[as], adst + part * A_BLK_BYTES,
+                                                         (part * P.DB + fb) * KBLK, m * TM);
+                                else tma_load_2d_pair(&map_a, &bars.a_full[as], adst + part * A_BLK_BYTES,
+                                                      (part * P.DB + fb) * KBLK, m * TM);
+                            }
+                            if (++as == NA) { as = 0; a_eph ^= 1; }
+                        }
 #pragma unroll
                         for (int part = 0; part < 2; ++part) {          // hi block, then lo block
                             mbar_wait(&bars.b_empty[bs], b_ph ^ 1);
-                            mbar_expect_tx(&bars.b_full[bs], B_BLK_BYTES);
-                            tma_load_2d(&map_b, &bars.b_full[bs], b_ring + (size_t)bs * B_BLK_BYTES,
-                                        (part * P.DB + fb) * KBLK, n * TN);
+                            if (rank == 0) mbar_expect_tx(&bars.b_full[bs], B_BLK_BYTES);
+                            uint8_t* dst = b_ring + (size_t)bs * B_STAGE;
+                            if (CG == 1) tma_load_2d(&map_b, &bars.b_full[bs], dst, (part * P.DB + fb) * KBLK, n * TN);
+                            else tma_load_2d_pair(&map_b, &bars.b_full[bs], dst, (part * P.DB + fb) * KBLK, n * TN + row_off);
                             if (++bs == NB) { bs = 0; b_ph ^= 1; }
                         }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         // ================================ MMA issuer ==================================
-        // warp-uniform control flow (operand descriptors stay in uniform registers); one elected lane issues
+        // warp-uniform control flow (operand descriptors stay in uniform registers); one elected lane issues.
+        // Pair mode: only the leader CTA issues; its commits arrive on the barriers of both CTAs.
         const bool leader = elect_one();
+        auto mma_wait = [&](uint64_t* bar, uint32_t parity) {
+            if (CG == 2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+        };
         const uint64_t adesc0 = umma_desc(smem_u32(a_ring));
         const uint64_t bdesc0 = umma_desc(smem_u32(b_ring));
         const uint64_t atdesc = umma_desc_sw32(smem_u32(a_tail));
         const uint64_t btdesc0 = umma_desc_sw32(smem_u32(t_ring));
         constexpr uint32_t A_SLOT_UNITS = (uint32_t)A_SLOT_BYTES >> 4;
         constexpr uint32_t A_LO_UNITS = (uint32_t)A_BLK_BYTES >> 4;
-        constexpr uint32_t B_UNITS = (uint32_t)B_BLK_BYTES >> 4;
-        constexpr uint32_t T_UNITS = (uint32_t)TAIL_B_BYTES >> 4;
+        constexpr uint32_t B_UNITS = (uint32_t)B_STAGE >> 4;
+        constexpr uint32_t T_UNITS = (uint32_t)T_STAGE >> 4;
         int as = 0, bs = 0, ts = 0;
         uint32_t a_ph = 0, b_ph = 0, t_ph = 0, j = 0;
-        for (int q = blockIdx.x; q < n_jobs; q += gridDim.x) {
-            if (ARES && q != (int)blockIdx.x) a_ph ^= 1;           // resident slots: one fill per job
+        for (int q = job0; q < n_jobs; q += job_stride) {
+            if (ARES && q != job0) a_ph ^= 1;                      // resident slots: one fill per job
             const int s = q % P.S;
             const int fb0 = s * P.fb_per_split;
             const int fb1 = min(P.DB, fb0 + P.fb_per_split);
             for (int n = 0; n < P.NT; ++n) {
-                mbar_wait(&bars.acc_empty[j & 1u], ((j >> 1) & 1u) ^ 1u);
+                mma_wait(&bars.acc_empty[j & 1u], ((j >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + (j & 1u) * TN;
                 uint32_t accum = 0;
                 if (s == 0) {
-                    mbar_wait(&bars.t_full[ts], t_ph);
+                    mma_wait(&bars.t_full[ts], t_ph);
                     tc_fence_after();
                     if (leader) {
-                        tc_mma_tf32(d_addr, atdesc, btdesc0 + (uint32_t)ts * T_UNITS, 0u);
-                        tc_commit(&bars.t_empty[ts]);
+                        tc_mma_tf32_cg<CG>(d_addr, atdesc, btdesc0 + (uint32_t)ts * T_UNITS, 0u);
+                        tc_commit_cg<CG>(&bars.t_empty[ts]);
                     }
                     accum = 1;
                     if (++ts == 2) { ts = 0; t_ph ^= 1; }
@@ -200,35 +250,35 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     if (ARES) as = fb;
                     const uint64_t ahi = adesc0 + (uint32_t)as * A_SLOT_UNITS;
                     const uint64_t alo = ahi + A_LO_UNITS;
-                    if (!ARES || n == 0) mbar_wait(&bars.a_full[as], a_ph);
-                    mbar_wait(&bars.b_full[bs], b_ph);
+                    if (!ARES || n == 0) mma_wait(&bars.a_full[as], a_ph);
+                    mma_wait(&bars.b_full[bs], b_ph);
                     tc_fence_after();
                     uint64_t bd = bdesc0 + (uint32_t)bs * B_UNITS;
                     if (leader) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < nks) tc_mma_tf32(d_addr, ahi + 2u * k, bd + 2u * k, accum | (uint32_t)(k > 0));
+                            if (k < nks) tc_mma_tf32_cg<CG>(d_addr, ahi + 2u * k, bd + 2u * k, accum | (uint32_t)(k > 0));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < nks) tc_mma_tf32(d_addr, alo + 2u * k, bd + 2u * k, 1u);
-                        tc_commit(&bars.b_empty[bs]);
+                            if (k < nks) tc_mma_tf32_cg<CG>(d_addr, alo + 2u * k, bd + 2u * k, 1u);
+                        tc_commit_cg<CG>(&bars.b_empty[bs]);
                     }
                     accum = 1;
                     if (++bs == NB) { bs = 0; b_ph ^= 1; }
-                    mbar_wait(&bars.b_full[bs], b_ph);
+                    mma_wait(&bars.b_full[bs], b_ph);
                     tc_fence_after();
                     bd = bdesc0 + (uint32_t)bs * B_UNITS;
                     if (leader) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < nks) tc_mma_tf32(d_addr, ahi + 2u * k, bd + 2u * k, 1u);
-                        tc_commit(&bars.b_empty[bs]);
-                        if (!ARES || n == P.NT - 1) tc_commit(&bars.a_empty[as]);
+                            if (k < nks) tc_mma_tf32_cg<CG>(d_addr, ahi + 2u * k, bd + 2u * k, 1u);
+                        tc_commit_cg<CG>(&bars.b_empty[bs]);
+                        if (!ARES || n == P.NT - 1) tc_commit_cg<CG>(&bars.a_empty[as]);
                     }
                     if (++bs == NB) { bs = 0; b_ph ^= 1; }
                     if (!ARES && ++as == NA) { as = 0; a_ph ^= 1; }
                 }
-                if (leader) tc_commit(&bars.acc_full[j & 1u]);
+                if (leader) tc_commit_cg<CG>(&bars.acc_full[j & 1u]);
                 ++j;
             }
         }
@@ -289,11 +339,11 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             }
         };
         // position in this CTA's (job, unit tile, feature block) stream
-        int q = blockIdx.x, n = 0, fb = 0, fb0 = 0, fb1 = 0;
+        int q = job0, n = 0, fb = 0, fb0 = 0, fb1 = 0;
         bool ok = false, live = q < n_jobs;
         const float* src = P.x;
         auto enter_job = [&]() {
-            const int s = q % P.S, m = q / P.S;
+            const int s = q % P.S, m = CG * (q / P.S) + (int)rank;
             fb0 = s * P.fb_per_split;
             fb1 = min(P.DB, fb0 + P.fb_per_split);
             fb = fb0;
@@ -306,7 +356,7 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         auto advance = [&]() {
             if (!live) return;
             if (ARES) {                       // resident mode: this group's block of the next job
-                q += gridDim.x;
+                q += job_stride;
                 if (q >= n_jobs) { live = false; return; }
                 enter_job();
                 fb = grp;
@@ -315,12 +365,13 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             if (++fb == fb1) {
                 fb = fb0;
                 if (++n == P.NT) {
-                    q += gridDim.x;
+                    q += job_stride;
                     if (q >= n_jobs) { live = false; return; }
                     enter_job();
                 }
             }
         };
+        if (P.a_tma) live = false;
         if (live) enter_job();
         if (ARES) {
             fb = grp;
@@ -356,7 +407,10 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.a_full[grp]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_remote(&bars.a_full[grp], 0);      // the leader's barrier counts both CTAs
+                else mbar_arrive(&bars.a_full[grp]);
+            }
             a_eph ^= 1;
             if (!more) break;
 #pragma unroll
@@ -368,8 +422,8 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         const int lg = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = lg * 32 + lane;             // patch row inside the tile
         uint32_t j = 0;
-        for (int q = blockIdx.x; q < n_jobs; q += gridDim.x) {
-            const int s = q % P.S, m = q / P.S;
+        for (int q = job0; q < n_jobs; q += job_stride) {
+            const int s = q % P.S, m = CG * (q / P.S) + (int)rank;
             const int64_t p = (int64_t)m * TM + row;
             float best = INFINITY;
             int bidx = 0;
@@ -408,7 +462,10 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                         // accumulator fully read: hand it back before the last reduction
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars.acc_empty[acc]);
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_remote(&bars.acc_empty[acc], 0);
+                            else mbar_arrive(&bars.acc_empty[acc]);
+                        }
                     }
                     consume(vb, c + 1);
                 }
@@ -423,9 +480,11 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();    // the peer may still multicast into / arrive on this CTA's shared memory
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -490,9 +549,49 @@ __global__ void __launch_bounds__(256) split_w_l_kernel(const float* __restrict_
     }
 }
 
+// CTA pairs (cta_group::2).  Static rule: pairs when there is no feature split and at least two waves of patch
+// tiles (measured: C4 7.44 -> 7.23 ms, C5 64.1 -> 62.1 ms; split-K shapes are faster unpaired).
+// SOM_TC_PAIR=0 / 1 forces the choice for A/B runs (read once per process).
+static int pair_mode() {
+    static int mode = -2;
+    if (mode == -2) { const char* e = getenv("SOM_TC_PAIR"); mode = e ? atoi(e) : -1; }
+    return mode;
+}
+
+// streamed mode pre-pass: patch rows p0 .. p0+rows-1 -> [ hi(x) for every 32-feature block | lo(x) for every block ],
+// zero beyond D; patchify fused as address arithmetic.  One thread per (patch, 4-feature group).
+__global__ void __launch_bounds__(256) split_x_l_kernel(const float* __restrict__ x, Geom g, int64_t p0, int64_t rows,
+                                                        int DB, float* __restrict__ Ap) {
+    const int groups = DB * 8;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= rows * groups) return;
+    const int64_t pr = t / groups;
+    const int d0 = (int)(t - pr * groups) * 4;
+    const float* src = x + patch_base(g, p0 + pr);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g.vec == 4 && d0 + 3 < g.D) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src + feat_off(g, d0)));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (d0 + e < g.D) v[e] = __ldg(src + feat_off(g, d0 + e));
+    }
+    float4 hi, lo;
+    hi.x = tf32_rna(v[0]); lo.x = tf32_rna(v[0] - hi.x);
+    hi.y = tf32_rna(v[1]); lo.y = tf32_rna(v[1] - hi.y);
+    hi.z = tf32_rna(v[2]); lo.z = tf32_rna(v[2] - hi.z);
+    hi.w = tf32_rna(v[3]); lo.w = tf32_rna(v[3] - hi.w);
+    float* dst = Ap + pr * (int64_t)DB * 64 + d0;
+    *reinterpret_cast<float4*>(dst) = hi;
+    *reinterpret_cast<float4*>(dst + (int64_t)DB * 32) = lo;
+}
+
 struct Plan {
+    int cg;
     int D, K, DB, nks_last, K_pad, NT, n_mtiles, S, fb_per_split;
-    size_t off_b, off_t, off_p, total;
+    int64_t chunk_rows;            // streamed mode: patches per pre-split workspace chunk (multiple of 128)
+    size_t off_b, off_t, off_p, off_a, total;
 };
 
 static void make_plan(Plan* pl, int64_t n, int D, int K) {
@@ -510,24 +609,35 @@ static void make_plan(Plan* pl, int64_t n, int D, int K) {
     if (S < 1) S = 1;
     pl->fb_per_split = (pl->DB + S - 1) / S;
     pl->S = (pl->DB + pl->fb_per_split - 1) / pl->fb_per_split;
+    pl->cg = 1;
+    if (sm_count() % 2 == 0 && pair_mode() != 0) {
+        if (pair_mode() == 1) pl->cg = 2;
+        else if (pl->S == 1 && pl->n_mtiles >= 2 * sm_count()) pl->cg = 2;
+    }
     size_t o = 0;
     pl->off_b = o; o = align_up(o + (size_t)pl->K_pad * pl->DB * 64 * 4, 1024);
     pl->off_t = o; o = align_up(o + (size_t)pl->K_pad * 8 * 4, 1024);
     pl->off_p = o;
     if (pl->S > 1) o = align_up(o + (size_t)pl->S * pl->n_mtiles * TM * pl->K_pad * 4, 1024);
+    pl->off_a = o;
+    pl->chunk_rows = 0;
+    if (pl->S == 1 && pl->DB > NA) {
+        // streamed mode: pre-split patch rows, chunked so that a chunk (~48 MB) stays L2 resident between the
+        // pre-pass and the GEMM kernel; whole waves of patch tiles per chunk
+        const int64_t row_bytes = (int64_t)pl->DB * 64 * 4;
+        const int64_t wave_rows = (int64_t)TM * sm_count();
+        int64_t max_rows = (48ll << 20) / row_bytes;
+        int64_t chunk = max_rows / wave_rows * wave_rows;
+        if (chunk < TM) chunk = (max_rows / TM > 0 ? max_rows / TM : 1) * TM;
+        const int64_t need = ceil_div64(n, TM) * TM;
+        if (chunk > need) chunk = need;
+        pl->chunk_rows = chunk;
+        o = align_up(o + (size_t)chunk * row_bytes, 1024);
+    }
     pl->total = o;
 }
 
 }  // namespace tcl
-
-// static rule: the fused-builder kernel is the split-K path (few patch tiles, long feature axis); with enough
-// patch tiles to fill the machine the TMA-fed path of som_bmu_tc.cu is faster (measured at config 5:
-// 80.7 ms vs 96 ms), so it keeps those shapes
-int tc_l_splits(int64_t n_patches, int D, int K) {
-    tcl::Plan pl;
-    tcl::make_plan(&pl, n_patches, D, K);
-    return pl.S;
-}
 
 size_t tc_l_workspace_bytes(int64_t n_patches, int D, int K) {
     tcl::Plan pl;
@@ -554,45 +664,89 @@ int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* 
         int rc = check_launch("split_w_l_kernel");
         if (rc) return rc;
     }
-    CUtensorMap map_b, map_t;
-    int rc = make_map2d(&map_b, Bp, (uint64_t)pl.K_pad, (uint64_t)pl.DB * 64, (uint64_t)pl.DB * 64 * 4, 32, TN,
+    CUtensorMap map_b, map_t, map_a;
+    const uint32_t box_rows = TN / pl.cg;
+    int rc = make_map2d(&map_b, Bp, (uint64_t)pl.K_pad, (uint64_t)pl.DB * 64, (uint64_t)pl.DB * 64 * 4, 32, box_rows,
                         CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map2d(&map_t, Tp, (uint64_t)pl.K_pad, 8, 32, 8, TN, CU_TENSOR_MAP_SWIZZLE_32B);
+    rc = make_map2d(&map_t, Tp, (uint64_t)pl.K_pad, 8, 32, 8, box_rows, CU_TENSOR_MAP_SWIZZLE_32B);
     if (rc) return rc;
+    const int mode = pl.S > 1 ? 0 : (pl.DB <= NA ? 1 : 2);          // split-K, resident-A, streamed
+    float* Ap = (float*)((char*)ws + pl.off_a);
+    map_a = map_b;                                                   // unused unless streamed
+    if (mode == 2) {
+        rc = make_map2d(&map_a, Ap, (uint64_t)pl.chunk_rows, (uint64_t)pl.DB * 64, (uint64_t)pl.DB * 64 * 4, 32, TM,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
 
     Params P;
     P.DB = pl.DB; P.nks_last = pl.nks_last; P.NT = pl.NT; P.n_mtiles = pl.n_mtiles; P.S = pl.S;
     P.fb_per_split = pl.fb_per_split; P.K_pad = pl.K_pad; P.rows = n; P.unit_offset = unit_offset;
     P.out_idx = out_idx; P.out_rd = out_rd; P.partial = pl.S > 1 ? Pp : nullptr; P.x = x; P.g = g;
+    P.a_tma = (mode == 2) ? 1 : 0; P.tile0 = 0;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SOM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
+
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+    static const KernelFn kernels[2][3] = {
+        {bmu_tc_l_kernel<true, false, 1>, bmu_tc_l_kernel<false, true, 1>, bmu_tc_l_kernel<false, false, 1>},
+        {bmu_tc_l_kernel<true, false, 2>, bmu_tc_l_kernel<false, true, 2>, bmu_tc_l_kernel<false, false, 2>}};
+    static const char* names[3] = {"bmu_tc_l_kernel<splitk>", "bmu_tc_l_kernel<resident>", "bmu_tc_l_kernel<streamed>"};
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(bmu_tc_l_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(bmu_tc_l_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(bmu_tc_l_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
+        for (int c = 0; c < 2; ++c)
+            for (int m = 0; m < 3; ++m) {
+                cudaError_t e = cudaFuncSetAttribute(kernels[c][m], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)SMEM_BYTES);
+                if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
+            }
         attr_done = true;
     }
-    const int n_jobs = pl.n_mtiles * pl.S;
-    const int grid = n_jobs < sm_count() ? n_jobs : sm_count();
+    auto launch = [&](const Params& Pl) -> int {
+        const int n_jobs = ((Pl.n_mtiles + pl.cg - 1) / pl.cg) * pl.S;
+        const int max_groups = sm_count() / pl.cg;
+        const int groups = n_jobs < max_groups ? n_jobs : max_groups;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(groups * pl.cg));
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)pl.cg;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, kernels[pl.cg - 1][mode], map_b, map_t, map_a, Pl);
+        if (le != cudaSuccess) { set_error("%s: launch: %s", names[mode], cudaGetErrorString(le)); return (int)le; }
+        return check_launch(names[mode]);
+    };
+    if (mode == 2) {
+        for (int64_t p0 = 0; p0 < n; p0 += pl.chunk_rows) {
+            const int64_t rows = (n - p0 < pl.chunk_rows) ? n - p0 : pl.chunk_rows;
+            const int64_t items = rows * pl.DB * 8;
+            split_x_l_kernel<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(x, g, p0, rows, pl.DB, Ap);
+            rc = check_launch("split_x_l_kernel");
+            if (rc) return rc;
+            Params Pc = P;
+            Pc.rows = rows;
+            Pc.n_mtiles = (int)ceil_div64(rows, TM);
+            Pc.out_idx = out_idx + p0;
+            Pc.out_rd = out_rd ? out_rd + p0 : nullptr;
+            rc = launch(Pc);
+            if (rc) return rc;
+        }
+        return SOM_OK;
+    }
+    rc = launch(P);
+    if (rc) return rc;
     if (pl.S > 1) {
-        bmu_tc_l_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
-        rc = check_launch("bmu_tc_l_kernel<splitk>");
-        if (rc) return rc;
         splitk_argmin_kernel<<<(unsigned)ceil_div64(n, 8), 256, 0, st>>>(Pp, pl.S, (int64_t)pl.n_mtiles * TM, pl.K_pad, K,
                                                                        n, unit_offset, out_idx, out_rd);
         return check_launch("splitk_argmin_kernel");
     }
-    if (pl.DB <= NA) {
-        bmu_tc_l_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
-        return check_launch("bmu_tc_l_kernel<resident>");
-    }
-    bmu_tc_l_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
-    return check_launch("bmu_tc_l_kernel");
+    return SOM_OK;
 }
 
 }  // namespace som

@@ -85,6 +85,98 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+// bounded wait with cluster-scope acquire (barriers that peer CTAs arrive on)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > (1u << 20)) __trap();
+    }
+}
+// TMA load issued by either CTA of a pair; the transaction bytes land on the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+// M = 128 * CG rows (one 128-row half per CTA), N = 256, K = 8, kind::tf32, K-major operands, fp32 accumulate
+template <int CG>
+__device__ __forceinline__ void tc_mma_tf32_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
+                               ((uint32_t)((TM * CG) >> 4) << 24);
+    if (CG == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+// commit: arrive (once the issued MMAs completed) on the barrier at this offset in every CTA of the pair
+template <int CG>
+__device__ __forceinline__ void tc_commit_cg(uint64_t* bar) {
+    if (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                     : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .b16 m;\n"
+            "mov.b16 m, 3;\n"
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+            "}\n" ::"r"(smem_u32(bar))
+            : "memory");
+    }
+}
+
 // one lane of a converged warp (elect.sync): the MMA warp keeps warp-uniform control flow, so descriptors
 // live in uniform registers, and only the tcgen05 instructions themselves are predicated on the elected lane
 __device__ __forceinline__ bool elect_one() {

@@ -198,17 +198,17 @@ def test_tensor_core_ties_inside_and_across_chunks():
         assert_bmu_parity(idx, ref, flat_patches(x, pd), w)
 
 
-@pytest.mark.parametrize("env", [{"SOM_TC_L": "2"}, {"SOM_TC_L": "0"}, {"SOM_TC_OLD_S": "1"}])
+@pytest.mark.parametrize("env", [{"SOM_TC_PAIR": "1"}, {"SOM_TC_PAIR": "0"}])
 def test_alternate_tensor_core_paths_in_a_subprocess(env):
-    """The static dispatch keeps some tensor-core kernels for specific shapes only (fused-builder kernel
-    in ARGMIN streaming mode, the TMA-fed configs M / L, the previous config S).  The override switches
-    are read once per process, so each alternative runs the parity probe in its own interpreter."""
+    """The static dispatch uses CTA pairs (cta_group::2) only for problems of at least two waves of patch
+    tiles.  The override switch is read once per process, so the forced-pair and forced-single variants run
+    the parity probe in their own interpreter on small shapes of every mode (resident-A, streamed, split-K)."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     probe = os.path.join(root, "tools", "tc_probe.py")
-    shapes = [("16", "8", "2048"), ("40", "4", "1000"), ("3", "8", "777"), ("64", "2", "4093")]
+    shapes = [("16", "8", "2048"), ("40", "4", "1000"), ("3", "8", "777"), ("64", "32", "512"), ("700", "4", "600")]
     for shp in shapes:
         r = subprocess.run([sys.executable, probe, *shp, "2"], env={**os.environ, **env},
                            capture_output=True, text=True, timeout=300)
