@@ -99,6 +99,9 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 const __grid_constant__ CUtensorMap map_a, const Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // unit tiles fed by one A-slot fill: split-K jobs use both TMEM accumulators for two unit tiles at once, which
+    // halves the builders' work per MMA (they are the bottleneck there); the other modes double-buffer one tile
+    constexpr int NI = SPLITK ? 2 : 1;
     constexpr int B_STAGE = B_BLK_BYTES / CG;       // this CTA's share of a 256-unit block
     constexpr int NB = B_RING_BYTES / B_STAGE;
     constexpr int T_STAGE = TAIL_B_BYTES / CG;
@@ -170,13 +173,17 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 const int s = q % P.S;
                 const int fb0 = s * P.fb_per_split;
                 const int fb1 = min(P.DB, fb0 + P.fb_per_split);
-                for (int n = 0; n < P.NT; ++n) {
+                for (int n0 = 0; n0 < P.NT; n0 += NI) {
+                    const int ni = min(NI, P.NT - n0);
                     if (s == 0) {
-                        mbar_wait(&bars.t_empty[ts], t_ph ^ 1);
-                        if (rank == 0) mbar_expect_tx(&bars.t_full[ts], TAIL_B_BYTES);
-                        if (CG == 1) tma_load_2d(&map_t, &bars.t_full[ts], t_ring + ts * T_STAGE, 0, n * TN);
-                        else tma_load_2d_pair(&map_t, &bars.t_full[ts], t_ring + ts * T_STAGE, 0, n * TN + row_off);
-                        if (++ts == 2) { ts = 0; t_ph ^= 1; }
+                        for (int a = 0; a < ni; ++a) {
+                            const int n = n0 + a;
+                            mbar_wait(&bars.t_empty[ts], t_ph ^ 1);
+                            if (rank == 0) mbar_expect_tx(&bars.t_full[ts], TAIL_B_BYTES);
+                            if (CG == 1) tma_load_2d(&map_t, &bars.t_full[ts], t_ring + ts * T_STAGE, 0, n * TN);
+                            else tma_load_2d_pair(&map_t, &bars.t_full[ts], t_ring + ts * T_STAGE, 0, n * TN + row_off);
+                            if (++ts == 2) { ts = 0; t_ph ^= 1; }
+                        }
                     }
                     for (int fb = fb0; fb < fb1; ++fb) {
                         if (P.a_tma) {
@@ -194,14 +201,17 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                             }
                             if (++as == NA) { as = 0; a_eph ^= 1; }
                         }
+                        for (int a = 0; a < ni; ++a) {
+                            const int n = n0 + a;
 #pragma unroll
-                        for (int part = 0; part < 2; ++part) {          // hi block, then lo block
-                            mbar_wait(&bars.b_empty[bs], b_ph ^ 1);
-                            if (rank == 0) mbar_expect_tx(&bars.b_full[bs], B_BLK_BYTES);
-                            uint8_t* dst = b_ring + (size_t)bs * B_STAGE;
-                            if (CG == 1) tma_load_2d(&map_b, &bars.b_full[bs], dst, (part * P.DB + fb) * KBLK, n * TN);
-                            else tma_load_2d_pair(&map_b, &bars.b_full[bs], dst, (part * P.DB + fb) * KBLK, n * TN + row_off);
-                            if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                            for (int part = 0; part < 2; ++part) {      // hi block, then lo block
+                                mbar_wait(&bars.b_empty[bs], b_ph ^ 1);
+                                if (rank == 0) mbar_expect_tx(&bars.b_full[bs], B_BLK_BYTES);
+                                uint8_t* dst = b_ring + (size_t)bs * B_STAGE;
+                                if (CG == 1) tma_load_2d(&map_b, &bars.b_full[bs], dst, (part * P.DB + fb) * KBLK, n * TN);
+                                else tma_load_2d_pair(&map_b, &bars.b_full[bs], dst, (part * P.DB + fb) * KBLK, n * TN + row_off);
+                                if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                            }
                         }
                     }
                 }
@@ -230,56 +240,75 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             const int s = q % P.S;
             const int fb0 = s * P.fb_per_split;
             const int fb1 = min(P.DB, fb0 + P.fb_per_split);
-            for (int n = 0; n < P.NT; ++n) {
-                mma_wait(&bars.acc_empty[j & 1u], ((j >> 1) & 1u) ^ 1u);
+            for (int n0 = 0; n0 < P.NT; n0 += NI) {
+                const int ni = min(NI, P.NT - n0);
+                uint32_t accum[NI];
+#pragma unroll
+                for (int a = 0; a < NI; ++a) {
+                    accum[a] = 0;
+                    if (a < ni) mma_wait(&bars.acc_empty[(j + a) & 1u], (((j + a) >> 1) & 1u) ^ 1u);
+                }
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + (j & 1u) * TN;
-                uint32_t accum = 0;
                 if (s == 0) {
-                    mma_wait(&bars.t_full[ts], t_ph);
-                    tc_fence_after();
-                    if (leader) {
-                        tc_mma_tf32_cg<CG>(d_addr, atdesc, btdesc0 + (uint32_t)ts * T_UNITS, 0u);
-                        tc_commit_cg<CG>(&bars.t_empty[ts]);
+#pragma unroll
+                    for (int a = 0; a < NI; ++a) {
+                        if (a < ni) {
+                            mma_wait(&bars.t_full[ts], t_ph);
+                            tc_fence_after();
+                            if (leader) {
+                                tc_mma_tf32_cg<CG>(tmem_base + ((j + a) & 1u) * TN, atdesc, btdesc0 + (uint32_t)ts * T_UNITS, 0u);
+                                tc_commit_cg<CG>(&bars.t_empty[ts]);
+                            }
+                            accum[a] = 1;
+                            if (++ts == 2) { ts = 0; t_ph ^= 1; }
+                        }
                     }
-                    accum = 1;
-                    if (++ts == 2) { ts = 0; t_ph ^= 1; }
                 }
                 for (int fb = fb0; fb < fb1; ++fb) {
                     const int nks = (fb == P.DB - 1) ? P.nks_last : 4;
                     if (ARES) as = fb;
                     const uint64_t ahi = adesc0 + (uint32_t)as * A_SLOT_UNITS;
                     const uint64_t alo = ahi + A_LO_UNITS;
-                    if (!ARES || n == 0) mma_wait(&bars.a_full[as], a_ph);
-                    mma_wait(&bars.b_full[bs], b_ph);
-                    tc_fence_after();
-                    uint64_t bd = bdesc0 + (uint32_t)bs * B_UNITS;
-                    if (leader) {
+                    if (!ARES || n0 == 0) mma_wait(&bars.a_full[as], a_ph);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < nks) tc_mma_tf32_cg<CG>(d_addr, ahi + 2u * k, bd + 2u * k, accum | (uint32_t)(k > 0));
+                    for (int a = 0; a < NI; ++a) {
+                        if (a < ni) {
+                            const uint32_t d_addr = tmem_base + ((j + a) & 1u) * TN;
+                            mma_wait(&bars.b_full[bs], b_ph);
+                            tc_fence_after();
+                            uint64_t bd = bdesc0 + (uint32_t)bs * B_UNITS;
+                            if (leader) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < nks) tc_mma_tf32_cg<CG>(d_addr, alo + 2u * k, bd + 2u * k, 1u);
-                        tc_commit_cg<CG>(&bars.b_empty[bs]);
+                                for (int k = 0; k < 4; ++k)
+                                    if (k < nks) tc_mma_tf32_cg<CG>(d_addr, ahi + 2u * k, bd + 2u * k, accum[a] | (uint32_t)(k > 0));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k < nks) tc_mma_tf32_cg<CG>(d_addr, alo + 2u * k, bd + 2u * k, 1u);
+                                tc_commit_cg<CG>(&bars.b_empty[bs]);
+                            }
+                            accum[a] = 1;
+                            if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                            mma_wait(&bars.b_full[bs], b_ph);
+                            tc_fence_after();
+                            bd = bdesc0 + (uint32_t)bs * B_UNITS;
+                            if (leader) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k < nks) tc_mma_tf32_cg<CG>(d_addr, ahi + 2u * k, bd + 2u * k, 1u);
+                                tc_commit_cg<CG>(&bars.b_empty[bs]);
+                            }
+                            if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                        }
                     }
-                    accum = 1;
-                    if (++bs == NB) { bs = 0; b_ph ^= 1; }
-                    mma_wait(&bars.b_full[bs], b_ph);
-                    tc_fence_after();
-                    bd = bdesc0 + (uint32_t)bs * B_UNITS;
-                    if (leader) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < nks) tc_mma_tf32_cg<CG>(d_addr, ahi + 2u * k, bd + 2u * k, 1u);
-                        tc_commit_cg<CG>(&bars.b_empty[bs]);
-                        if (!ARES || n == P.NT - 1) tc_commit_cg<CG>(&bars.a_empty[as]);
-                    }
-                    if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                    if (leader && (!ARES || n0 + ni >= P.NT)) tc_commit_cg<CG>(&bars.a_empty[as]);
                     if (!ARES && ++as == NA) { as = 0; a_ph ^= 1; }
                 }
-                if (leader) tc_commit_cg<CG>(&bars.acc_full[j & 1u]);
-                ++j;
+                if (leader) {
+#pragma unroll
+                    for (int a = 0; a < NI; ++a)
+                        if (a < ni) tc_commit_cg<CG>(&bars.acc_full[(j + a) & 1u]);
+                }
+                j += (uint32_t)ni;
             }
         }
     } else if (warp >= BUILD_WARP0 && warp < BUILD_WARP0 + BUILD_WARPS) {
@@ -364,7 +393,7 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             }
             if (++fb == fb1) {
                 fb = fb0;
-                if (++n == P.NT) {
+                if ((n += NI) >= P.NT) {
                     q += job_stride;
                     if (q >= n_jobs) { live = false; return; }
                     enter_job();
