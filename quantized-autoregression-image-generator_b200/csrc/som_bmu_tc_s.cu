@@ -87,8 +87,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
 }
 
 __device__ long long g_prof[4];              // CTA 0: cycles of the MMA loop, tiles issued
-__device__ long long g_tl6[2][64];
-__device__ long long g_tl[6][64];            // SOM_TC_DEBUG & 64: timeline of tiles 200..263 of CTA 0
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
@@ -346,8 +344,6 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                         const uint32_t acc = j & 1u;
                         mbar_wait(&bars.acc_full[acc], (j >> 1) & 1u);
                         tc_fence_after();
-                        const bool tlrec = (P.dbg & 64) && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && j >= 200 && j < 264;
-                        if (tlrec) g_tl[4][j - 200] = clock64();
                         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TN + (uint32_t)half * 128u;
                         const int col0 = n * TN + half * 128;
                         uint32_t va[32], vb[32];
@@ -383,7 +379,6 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars.acc_empty[acc]);
-                        if (tlrec) g_tl[5][j - 200] = clock64();
                         consume(vb, 3);
                         ++j;
                     }
@@ -511,10 +506,6 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
 }  // namespace som
 
 // debug: cycles spent by CTA 0's MMA issue loop and the tiles it issued in the last config-S launch
-extern "C" SOM_API int som_debug_tc_timeline(long long* out512) {
-    cudaMemcpyFromSymbol(out512 + 384, som::tcs::g_tl6, 2 * 64 * sizeof(long long));
-    return (int)cudaMemcpyFromSymbol(out512, som::tcs::g_tl, 6 * 64 * sizeof(long long));
-}
 extern "C" SOM_API int som_debug_tc_cycles(long long* out2) {
     return (int)cudaMemcpyFromSymbol(out2, som::tcs::g_prof, 2 * sizeof(long long));
 }

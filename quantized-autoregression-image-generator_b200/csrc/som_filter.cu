@@ -87,6 +87,85 @@ filter_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int 
     }
 }
 
+// Tiled variant (D % 4 == 0, D >= 48, 16-byte aligned rows).  The scalar kernel above waits a full L2 round trip
+// per group of TA rows; here a CTA owns 64 units x 64 features, streams the input rows it needs through shared
+// memory in coalesced 64-row chunks, and every thread keeps a 4 x 4 register tile: 4 LDS.128 + 7 table reads
+// per 64 FFMAs.  Same summation order per output as the scalar kernel (ascending j; rows outside a unit's band
+// meet an exactly-zero weight).
+constexpr int FT_TK = 64, FT_TD = 64, FT_JC = 64, FT_THREADS = 256;
+constexpr int FT_PAD = FT_TK + FT_JC + 8;
+
+__global__ void __launch_bounds__(FT_THREADS)
+filter_tile_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int D,
+                   float two_var, int h, float scale) {
+    extern __shared__ float fsm[];
+    const int off = h + FT_PAD;
+    const int tab_n = 2 * off + 1;
+    float* tab = fsm;
+    float4* chunk = reinterpret_cast<float4*>(fsm + ((tab_n + 3) & ~3));         // [FT_JC][FT_TD / 4]
+    for (int i = threadIdx.x; i < tab_n; i += FT_THREADS) {
+        int t = i - off;
+        int at = t < 0 ? -t : t;
+        float w = 0.f;
+        if (at <= h) {
+            float sq = (float)((long long)at * (long long)at);
+            w = expf(-(__fdiv_rn(sq, two_var)));
+        }
+        tab[i] = w;
+    }
+    const int a_tile = blockIdx.x * FT_TK;
+    const int d_tile = blockIdx.y * FT_TD;
+    const int ug = threadIdx.x >> 4, fg = threadIdx.x & 15;
+    const int a0 = a_tile + 4 * ug;
+    int j_lo = a_tile - h; if (j_lo < 0) j_lo = 0;
+    int j_hi = a_tile + FT_TK - 1 + h; if (j_hi > K - 1) j_hi = K - 1;
+
+    float4 acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int jc = j_lo; jc <= j_hi; jc += FT_JC) {
+        __syncthreads();                                    // table ready / previous chunk consumed
+#pragma unroll
+        for (int i = 0; i < FT_JC * (FT_TD / 4) / FT_THREADS; ++i) {
+            const int idx = threadIdx.x + FT_THREADS * i;
+            const int r = idx >> 4, c4 = idx & 15;
+            const int j = jc + r, d = d_tile + 4 * c4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j <= j_hi && d < D) v = __ldg(reinterpret_cast<const float4*>(in + (int64_t)j * D + d));
+            chunk[idx] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < FT_JC; r += 4) {
+            const int t0 = (jc + r) - a0 + off;             // weight index of (row jc + r, unit a0)
+            float wv[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) wv[q] = tab[t0 - 3 + q];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 v = chunk[(r + u) * (FT_TD / 4) + fg];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float w = wv[u - i + 3];          // w(|(jc + r + u) - (a0 + i)|)
+                    acc[i].x = fmaf(w, v.x, acc[i].x);
+                    acc[i].y = fmaf(w, v.y, acc[i].y);
+                    acc[i].z = fmaf(w, v.z, acc[i].z);
+                    acc[i].w = fmaf(w, v.w, acc[i].w);
+                }
+            }
+        }
+    }
+    const int d = d_tile + 4 * fg;
+    if (d < D) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (a0 + i < K)
+                *reinterpret_cast<float4*>(out + (int64_t)(a0 + i) * D + d) =
+                    make_float4(scale * acc[i].x, scale * acc[i].y, scale * acc[i].z, scale * acc[i].w);
+    }
+}
+
 // largest t with expf(-(float(t*t)/two_var)) > 0, found on the host with the same fp32 steps
 static int host_band_half_width(float two_var, int K) {
     // expf underflows to 0 below about -103.98; search a small window around that root
@@ -125,6 +204,21 @@ extern "C" int som_filter_f32(const float* in, float* out, int K, int D,
                                              200 * 1024);
         if (e != cudaSuccess) { set_error("filter: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
+    }
+    if ((D & 3) == 0 && D >= 48 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+        const size_t tab_n = (size_t)(2 * (h + FT_PAD) + 1);
+        const size_t smem_t = ((tab_n + 3) & ~(size_t)3) * sizeof(float) + (size_t)FT_JC * FT_TD * sizeof(float);
+        SOM_REQUIRE(smem_t <= 200 * 1024, SOM_E_SHAPE, "filter: band half-width %d too large", h);
+        static bool attr_t = false;
+        if (smem_t > 48 * 1024 && !attr_t) {
+            cudaError_t e = cudaFuncSetAttribute(filter_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 200 * 1024);
+            if (e != cudaSuccess) { set_error("filter: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
+            attr_t = true;
+        }
+        dim3 gt((unsigned)ceil_div64(K, FT_TK), (unsigned)ceil_div64(D, FT_TD));
+        filter_tile_kernel<<<gt, FT_THREADS, smem_t, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);
+        return check_launch("filter_tile_kernel");
     }
     dim3 grid((unsigned)ceil_div64(K, FILT_WARPS * FILT_TA), (unsigned)ceil_div64(D, 32));
     filter_kernel<<<grid, FILT_WARPS * 32, smem, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);

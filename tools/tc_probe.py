@@ -56,12 +56,6 @@ try:
     lib = somcb._lib.load()
     if lib.som_debug_tc_cycles(cyc) == 0 and cyc[1] > 0 and d <= 16 and variant == 2:
         print(f"  [config S] CTA0 MMA loop: {cyc[0] / cyc[1]:.0f} cycles per 128x256 tile over {cyc[1]} tiles", flush=True)
-    if os.environ.get("SOM_TC_DEBUG") and int(os.environ["SOM_TC_DEBUG"]) & 64:
-        tl = (ctypes.c_longlong * 512)()
-        lib.som_debug_tc_timeline(tl)
-        t0 = tl[0]
-        for i in range(40):
-            print(f"  [tl] tile {i}: iter_begin {tl[i]-t0} tests_begin {tl[64+i]-t0} tests_done {tl[384+i]-t0} last_mma_issued {tl[448+i]-t0} committed {tl[128+i]-t0} ok={tl[192+i]} | epi_full_seen {tl[256+i]-t0} epi_arrive {tl[320+i]-t0}")
 except Exception as e:  # noqa: BLE001
     print("  (no cycle probe:", e, ")")
 print(f"  OK: {nbad} near-tie diffs vs oracle on {flat.shape[0]} patches, {diff} diffs vs FFMA on {npat}; "
