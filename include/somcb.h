@@ -121,6 +121,11 @@ SOM_API int som_quantize_nchw_f32(const int64_t* idx, const float* table, int K,
 SOM_API int som_adam_f32(float* W, float* m, float* v, const float* g, int64_t n,
                  double lr, double b1, double b2, double eps, int64_t step, void* stream);
 
+/* Same update with the step count kept in DEVICE memory (for CUDA-graph replay of the training
+ * step): uses t = *steps_done + 1, then increments *steps_done on the stream.               */
+SOM_API int som_adam_devstep_f32(float* W, float* m, float* v, const float* g, int64_t n,
+                         double lr, double b1, double b2, double eps, int64_t* steps_done, void* stream);
+
 /* ---- row compaction for pruning ----------------------------------------------------------
  * out[r] = W[keep[r]] for r < n_keep (prune_codebook.py:161-162).                        */
 SOM_API int som_gather_rows_f32(const float* W, int D, const int64_t* keep, int64_t n_keep,

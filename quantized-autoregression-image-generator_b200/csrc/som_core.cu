@@ -212,6 +212,30 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ W, float*
     }
 }
 
+// Same rule with the step count read from device memory, so a captured CUDA graph of the training step can be
+// replayed: t = *steps_done + 1; bias corrections in double as on the host path.  step_bump_kernel advances it.
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ W, float* __restrict__ m,
+                                                       float* __restrict__ v, const float* __restrict__ g,
+                                                       int64_t n, double lr, double b1, double b2, float eps,
+                                                       const int64_t* __restrict__ steps_done) {
+    const double t = (double)(*steps_done + 1);
+    const float w1 = (float)(1.0 - b1), b2f = (float)b2, one_m_b2 = (float)(1.0 - b2);
+    const float step_size = (float)(lr / (1.0 - pow(b1, t)));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow(b2, t));
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gi = g[i], mi = m[i], vi = v[i];
+        float diff = gi - mi;
+        mi = (w1 < 0.5f) ? __fmaf_rn(w1, diff, mi) : __fmaf_rn(-diff, 1.0f - w1, gi);
+        vi = __fmaf_rn(one_m_b2 * gi, gi, vi * b2f);
+        float denom = __fdiv_rn(__fsqrt_rn(vi), bc2_sqrt) + eps;
+        W[i] = __fmaf_rn(-step_size, __fdiv_rn(mi, denom), W[i]);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+__global__ void step_bump_kernel(int64_t* steps_done) { *steps_done += 1; }
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ W, int D,
                                                           const int64_t* __restrict__ keep,
                                                           int64_t n_keep, float* __restrict__ out) {
@@ -342,6 +366,20 @@ int som_adam_f32(float* W, float* m, float* v, const float* g, int64_t n,
         W, m, v, g, n, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2),
         (float)step_size, (float)bc2_sqrt, (float)eps);
     return check_launch("adam_kernel");
+}
+
+int som_adam_devstep_f32(float* W, float* m, float* v, const float* g, int64_t n,
+                         double lr, double b1, double b2, double eps, int64_t* steps_done, void* stream) {
+    SOM_REQUIRE(W && m && v && g && steps_done, SOM_E_BADARG, "adam(devstep): null pointer");
+    SOM_REQUIRE(n >= 0, SOM_E_BADARG, "adam(devstep): n=%lld", (long long)n);
+    if (n > 0) {
+        int blocks = grid_for(n, 256, 16);
+        adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, m, v, g, n, lr, b1, b2, (float)eps, steps_done);
+        int rc = check_launch("adam_dev_kernel");
+        if (rc) return rc;
+    }
+    step_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(steps_done);
+    return check_launch("step_bump_kernel");
 }
 
 int som_gather_rows_f32(const float* W, int D, const int64_t* keep, int64_t n_keep,

@@ -35,6 +35,8 @@ SIGNATURES = {
                                       c_int, c_int, c_void_p, c_void_p]),
     "som_adam_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                              c_double, c_double, c_int64, c_void_p]),
+    "som_adam_devstep_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
+                                     c_double, c_double, c_void_p, c_void_p]),
     "som_gather_rows_f32": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "som_assemble_tokens_i64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_int,
                                         c_void_p, c_void_p, c_void_p]),

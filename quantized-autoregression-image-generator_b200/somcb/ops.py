@@ -209,6 +209,21 @@ def adam_step(weight, m, v, grad, lr, step, betas=(0.5, 0.999), eps=1e-8):
     return weight
 
 
+def adam_step_dev(weight, m, v, grad, lr, steps_done, betas=(0.5, 0.999), eps=1e-8):
+    """K4 with the step count in device memory (``steps_done``: int64 tensor of one element, the
+    number of completed steps); increments it on the stream.  Used under CUDA-graph capture."""
+    lib = _lib.load()
+    for t, nm in ((weight, "weight"), (m, "m"), (v, "v"), (grad, "grad")):
+        _req(t, torch.float32, nm)
+    _req(steps_done, torch.int64, "steps_done")
+    with torch.cuda.device(weight.device):
+        check("som_adam_devstep_f32",
+              lib.som_adam_devstep_f32(_ptr(weight), _ptr(m), _ptr(v), _ptr(grad), weight.numel(), float(lr),
+                                       float(betas[0]), float(betas[1]), float(eps), _ptr(steps_done),
+                                       _stream(weight)))
+    return weight
+
+
 def gather_rows(weight, keep):
     lib = _lib.load()
     w = _req(weight, torch.float32, "weight")

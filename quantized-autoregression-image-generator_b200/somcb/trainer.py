@@ -22,9 +22,17 @@ from . import ops as _default_ops
 
 class SomTrainer:
     def __init__(self, codebook, lr, neighbourhood_step, lr_step=100000, global_steps=0,
-                 betas=(0.5, 0.999), eps=1e-8, ops=None, reduce_fn=None, world_size=1):
+                 betas=(0.5, 0.999), eps=1e-8, ops=None, reduce_fn=None, world_size=1,
+                 use_cuda_graph=False):
         """``codebook``: a somcb.Codebook on a CUDA device.  ``reduce_fn(list_of_tensors)`` sums
-        tensors in place across data-parallel ranks (None: single device)."""
+        tensors in place across data-parallel ranks (None: single device).
+
+        ``use_cuda_graph``: small batches (BASELINE config 1: 512 patches per step) are bound by the
+        ~10 launches of a step, not by the kernels.  With this flag the step is captured once per
+        (batch shape, neighbourhood range, lr) into a CUDA graph and replayed: the batch is copied
+        into a static buffer, Adam's step count lives in device memory (``som_adam_devstep_f32``).
+        Single-device only; the first step always runs eagerly (it performs the one-time kernel
+        attribute set-up that must not happen during capture)."""
         self.cb = codebook
         self.lr = float(lr)
         self.neighbourhood_step = int(neighbourhood_step)
@@ -41,11 +49,46 @@ class SomTrainer:
         self.v = torch.zeros_like(w, requires_grad=False)
         self.t = 0
         self.last_bmu = None
+        self.use_cuda_graph = bool(use_cuda_graph) and reduce_fn is None
+        self._graph = None            # (key, CUDAGraph, x_static, loss_static, t_dev)
 
     @torch.no_grad()
     def step(self, feature_map, bmu=None):
         """One training step on a (local) batch; returns the loss as a 0-dim float64 device
         tensor (global mean squared error, as F.mse_loss over the global batch)."""
+        if self.use_cuda_graph and bmu is None and self.t >= 1 and feature_map.is_cuda:
+            return self._graph_step(feature_map)
+        return self._eager_step(feature_map, bmu)
+
+    def _graph_step(self, feature_map):
+        cb = self.cb
+        key = (tuple(feature_map.shape), float(cb.neighbourhood_range), float(self.lr))
+        if self._graph is None or self._graph[0] != key:
+            x_static = torch.empty(feature_map.shape, dtype=torch.float32, device=feature_map.device)
+            t_dev = torch.full((1,), self.t, dtype=torch.int64, device=feature_map.device)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(feature_map.device)
+            with torch.cuda.graph(graph):
+                loss_static = self._eager_step(x_static, None, t_dev=t_dev, bookkeeping=False)
+            self._graph = (key, graph, x_static, loss_static, t_dev)
+        _, graph, x_static, loss_static, t_dev = self._graph
+        x_static.copy_(feature_map)
+        graph.replay()
+        self.t += 1
+        cb._norm_cache = None
+        self.last_bmu = None
+        self._bookkeeping()
+        return loss_static.clone()
+
+    def _bookkeeping(self):
+        # schedule bookkeeping, in the reference's order (train_codebook.py:247-249, 300-304)
+        if self.global_steps % self.lr_step == 0 and self.global_steps > 0:
+            self.lr = self.lr * 0.5
+        self.global_steps += 1
+        if self.global_steps % self.neighbourhood_step == 0:
+            self.cb.decrease_neighbourhood(steps=1)
+
+    def _eager_step(self, feature_map, bmu=None, t_dev=None, bookkeeping=True):
         ops = self.ops
         cb = self.cb
         w = cb.codebook.weight.data
@@ -72,18 +115,16 @@ class SomTrainer:
             self.reduce_fn(packed)
             sse = packed[kd:kd + 1].double() + packed[kd + 1:kd + 2].double()
         grad = ops.neighbourhood_filter(rbar, rng, scale=2.0 / numel)
-        self.t += 1
-        ops.adam_step(w, self.m, self.v, grad, self.lr, self.t, self.betas, self.eps)
+        if t_dev is not None:                          # graph capture: step count in device memory
+            ops.adam_step_dev(w, self.m, self.v, grad, self.lr, t_dev, self.betas, self.eps)
+        else:
+            self.t += 1
+            ops.adam_step(w, self.m, self.v, grad, self.lr, self.t, self.betas, self.eps)
         cb._norm_cache = None                          # W changed under torch's feet
         self.last_bmu = bmu
         loss = (sse / numel).reshape(())
-
-        # schedule bookkeeping, in the reference's order (train_codebook.py:247-249, 300-304)
-        if self.global_steps % self.lr_step == 0 and self.global_steps > 0:
-            self.lr = self.lr * 0.5
-        self.global_steps += 1
-        if self.global_steps % self.neighbourhood_step == 0:
-            cb.decrease_neighbourhood(steps=1)
+        if bookkeeping:
+            self._bookkeeping()
         return loss
 
     def checkpoint_dict(self, image_channel):

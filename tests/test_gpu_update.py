@@ -197,3 +197,28 @@ def test_adam_kernel_matches_torch_adam():
         opt.step()
         ops.adam_step(w, m, v, grad.to(DEV), 3e-3, t)
         assert rel_fro(w, p.detach()) <= 2e-7
+
+
+def test_cuda_graph_trainer_matches_eager_trainer():
+    """SomTrainer(use_cuda_graph=True): 60 steps of config 1 with the neighbourhood range shrinking every 20
+    steps (forces two re-captures) against the eager fused trainer -- same losses and weights."""
+    from oracle.step_oracle import synthetic_fmaps, trained_like_codebook
+    pd, k = (4, 4), 1024
+    w0 = trained_like_codebook(k, pd, 7)
+    trainers = []
+    for graph in (False, True):
+        cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                            init_neighbour_range=k // 2)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(w0)
+        cb = cb.to(DEV)
+        trainers.append(somcb.SomTrainer(cb, lr=1e-4, neighbourhood_step=20, use_cuda_graph=graph))
+    for step in range(60):
+        x = synthetic_fmaps(8, 123 + step).to(DEV)
+        l0 = float(trainers[0].step(x))
+        l1 = float(trainers[1].step(x))
+        assert abs(l0 - l1) <= 1e-6 * abs(l0), f"step {step}: loss {l0} vs {l1}"
+    assert trainers[1]._graph is not None and trainers[1].t == 60
+    assert trainers[0].cb.neighbourhood_range == trainers[1].cb.neighbourhood_range == k // 2 - 3
+    assert_close_norm(trainers[1].cb.codebook.weight.data, trainers[0].cb.codebook.weight.data,
+                      what="weights after 60 graph-replayed steps")

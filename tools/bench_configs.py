@@ -112,6 +112,10 @@ def main():
             t_s = timed(lambda: tr.step(x), reps)
             row["step"] = {"ms": t_s, "patches_per_s": n / t_s * 1e3,
                            "sum_of_kernels_ms": ms + 2 * t_f + t_a + t_ad + t_n}
+            if n <= 65536:                          # launch-bound shapes: CUDA-graph replay of the step
+                trg = somcb.SomTrainer(cb, lr=1e-4, neighbourhood_step=10 ** 9, use_cuda_graph=True)
+                t_g = timed(lambda: trg.step(x), max(reps, 50), warm=5)
+                row["step_cuda_graph"] = {"ms": t_g, "patches_per_s": n / t_g * 1e3}
         else:
             idx = ops.bmu(x, geom, wd, cn)
             t_h = timed(lambda: ops.histogram(idx, k), reps)
