@@ -24,6 +24,11 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# NCCL prints "NCCL version ..." on STDOUT at NCCL_DEBUG=VERSION (and INFO); the contract is ONE JSON line there.
+# An explicit INFO / TRACE request is left alone.
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 METRIC = "patches/sec BMU (fine-patch tokenisation P=2 D=16 K=4096, 10M patches/step/GPU)"
