@@ -485,6 +485,8 @@ extern "C" int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int
     int vec = g.vec;
     if (Wt != nullptr && ((uintptr_t)Wt & 15) != 0) vec = 1;
     if (((uintptr_t)Rbar & 15) != 0) vec = 1;
+    // a warp covers 32 * vec features of one patch row: keep all lanes busy for short rows (C4, D = 64: vec 2)
+    while (vec > 1 && 32 * vec > g.D) vec >>= 1;
     if (vec == 4) return launch_levels<4>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
     if (vec == 2) return launch_levels<2>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
     return launch_levels<1>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);

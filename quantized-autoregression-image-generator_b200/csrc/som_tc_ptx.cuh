@@ -302,20 +302,6 @@ static inline EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static inline int make_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, uint32_t box_rows) {
-    EncodeTiledFn fn = get_encode_fn();
-    SOM_REQUIRE(fn != nullptr, SOM_E_UNSUPPORTED, "bmu(tc): cuTensorMapEncodeTiled is not available");
-    cuuint64_t dims[2] = {kp, rows};
-    cuuint64_t strides[1] = {kp * 4};
-    cuuint32_t box[2] = {KBLK, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SOM_REQUIRE(r == CUDA_SUCCESS, SOM_E_UNSUPPORTED, "bmu(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return SOM_OK;
-}
-
 // general 2-D fp32 tensor map: `cols` floats per row (row pitch `pitch_bytes`), box = box_cols x box_rows
 static inline int make_map2d(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                              uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
