@@ -88,7 +88,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def __enter__(self):
         if self.nv is not None:

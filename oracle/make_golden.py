@@ -161,6 +161,33 @@ def main():
     ck = {"patch_dim": pd, "image_dim": (32, 32), "image_C": 4, "num_embeddings": k,
           "neighbourhood_range": 128, "global_steps": 17, "checkpoint": cb.state_dict()}
     torch.save(ck, os.path.join(out_dir, "reference_checkpoint.pt"))
+
+    # ---- dual-codebook token assembly (train_quantized_transformer.py:407-455) -----------
+    # The script cannot be imported here (tinydb is not installed), so its OWN lines are read from
+    # the reference tree at generation time, dedented and executed on reference Codebook modules:
+    # the golden outputs come from the reference's code, which is never copied into this repository.
+    import textwrap
+    with open(os.path.join(REF, "train_quantized_transformer.py")) as f:
+        src_lines = f.read().splitlines()
+    snippet = textwrap.dedent("\n".join(src_lines[406:455]))         # lines 407-455 of the training loop
+    assert "lr_codebook.get_patches_bmu" in snippet and "hr_target = hr_target.to(device)" in snippet
+    xt = synthetic_fmaps(6, 777)
+    lr_w = trained_like_codebook(96, (8, 8), 31)
+    hr_w = trained_like_codebook(160, (4, 4), 32)
+    rec = {"x": xt, "lr_weight": lr_w, "hr_weight": hr_w, "lr_patch": (8, 8), "hr_patch": (4, 4),
+           "image_dim": (32, 32), "channels": 4}
+    for base in (True, False):
+        env = {"torch": torch, "device": torch.device("cpu"), "feature_map": xt, "train_base_model": base,
+               "lr_codebook": _build(Codebook, lr_w, (8, 8), (32, 32), 4, 48),
+               "hr_codebook": _build(Codebook, hr_w, (4, 4), (32, 32), 4, 80),
+               "lr_num_embeddings": 96, "hr_num_embeddings": 160}
+        exec(compile(snippet, "train_quantized_transformer.py[407:455]", "exec"), env)
+        tag = "base" if base else "cond"
+        rec[f"hr_input_{tag}"] = env["hr_input"].clone()
+        rec[f"hr_target_{tag}"] = env["hr_target"].clone()
+        rec[f"lr_input_{tag}"] = None if env["lr_input"] is None else env["lr_input"].clone()
+    torch.save(rec, os.path.join(out_dir, "tokens_case.pt"))
+    print("tokens:", tuple(rec["hr_input_base"].shape), tuple(rec["hr_input_cond"].shape))
     print("done ->", out_dir)
 
 

@@ -1,9 +1,10 @@
 """CPU restatement of the dual-codebook tokenisation of the Transformer trainer.  TEST INFRASTRUCTURE ONLY.
 
 Follows /root/reference/train_quantized_transformer.py:411-455 with the reference's own torch
-calls (cat / repeat / add), on OracleCodebook modules.  The reference ships no vectors for it
-(parity unpinned beyond the BMU goldens the two index tensors already rest on): the assembly
-is pure integer copying, checked bit-exactly.
+calls (cat / repeat / add), on OracleCodebook modules.  Pinned: oracle/make_golden.py executes the
+reference script's own lines 407-455 (read from the reference tree at generation time, never copied
+here) on reference Codebook modules and commits tests/golden/tokens_case.pt;
+tests/test_oracle_golden.py checks this restatement against it bit-exactly.
 """
 import torch
 

@@ -205,3 +205,23 @@ def test_shard_reader_feeds_host_tokenizer(tmp_path):
         assert torch.equal(idx, ref[lo:hi])
         counts = ops.histogram(idx.to(DEV).reshape(-1), k, counts)
     assert torch.equal(counts.cpu(), torch.bincount(ref.reshape(-1), minlength=k))
+
+
+def test_tokenize_pair_matches_reference_golden():
+    """GPU tokeniser against the outputs of the reference script's own lines (tests/golden/tokens_case.pt)."""
+    rec = load_golden("tokens_case.pt")
+    cbs = []
+    for wkey, pkey in (("lr_weight", "lr_patch"), ("hr_weight", "hr_patch")):
+        w = rec[wkey]
+        cb = somcb.Codebook(patch_dim=rec[pkey], image_dim=rec["image_dim"], image_channel=rec["channels"],
+                            num_embeddings=w.shape[0], init_neighbour_range=w.shape[0] // 2)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(w)
+        cbs.append(cb.to(DEV).eval())
+    for base, tag in ((True, "base"), (False, "cond")):
+        hi, ht, li = somcb.tokenize_pair(cbs[0], cbs[1], rec["x"].to(DEV), base)
+        assert torch.equal(hi.cpu(), rec[f"hr_input_{tag}"]) and torch.equal(ht.cpu(), rec[f"hr_target_{tag}"])
+        if rec[f"lr_input_{tag}"] is None:
+            assert li is None
+        else:
+            assert torch.equal(li.cpu(), rec[f"lr_input_{tag}"])

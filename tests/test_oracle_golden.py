@@ -130,3 +130,20 @@ def test_token_assembly_oracle_shapes_and_tokens():
     hi2, ht2, li2 = tokenize_pair_oracle(lr, hr, x, False)
     assert hi2.shape == (3, 65) and bool((hi2[:, 0] == 70).all()) and torch.equal(hi2[:, 1:], ht2[:, :-1])
     assert torch.equal(li2, hi[:, :16]) and torch.equal(ht, ht2)
+
+
+def test_token_assembly_oracle_matches_reference_golden():
+    """tokens_case.pt holds the outputs of the reference script's own lines 407-455."""
+    from oracle import tokenize_pair_oracle
+    from oracle.step_oracle import make_oracle_codebook
+    from _helpers import load_golden
+    rec = load_golden("tokens_case.pt")
+    lr = make_oracle_codebook(rec["lr_weight"], rec["lr_patch"], rec["image_dim"], rec["channels"], 48)
+    hr = make_oracle_codebook(rec["hr_weight"], rec["hr_patch"], rec["image_dim"], rec["channels"], 80)
+    for base, tag in ((True, "base"), (False, "cond")):
+        hi, ht, li = tokenize_pair_oracle(lr, hr, rec["x"], base)
+        assert torch.equal(hi, rec[f"hr_input_{tag}"]) and torch.equal(ht, rec[f"hr_target_{tag}"])
+        if rec[f"lr_input_{tag}"] is None:
+            assert li is None
+        else:
+            assert torch.equal(li, rec[f"lr_input_{tag}"])
