@@ -202,6 +202,63 @@ def _extra_training(dev, world, rank, group):
             "patches_per_s": world * n_f * 64 / (ms * 1e-3), "ms_per_step": ms, "loss": float(loss)}
 
 
+def _extra_configs(dev):
+    """Single-GPU timings of the other BASELINE shapes (device time, CUDA events): C1 step with CUDA-graph
+    replay, C3 BMU + full step, C5 one GPU's shard BMU.  Reported beside the headline, not part of it."""
+    import somcb
+    from somcb import ops
+
+    def data(n, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        x = torch.empty(n, 4, 32, 32, device=dev)
+        for lo in range(0, n, 8192):
+            hi = min(n, lo + 8192)
+            x[lo:hi] = torch.tanh(torch.randn(hi - lo, 4, 32, 32, generator=g, device=dev))
+        return x
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def codebook(k, pd, rng):
+        d = 4 * pd[0] * pd[1]
+        pool = data(max(8, (k * d) // 4096 + 1), 7)
+        w = somcb.patchify(pool, pd).reshape(-1, d)[:k].contiguous()
+        cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                            init_neighbour_range=rng).to(dev)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(w)
+        return cb
+
+    out = {}
+    x1, cb1 = data(8, 123), codebook(1024, (4, 4), 512)
+    tr1 = somcb.SomTrainer(cb1, lr=1e-4, neighbourhood_step=10 ** 9, use_cuda_graph=True)
+    out["C1_step_cuda_graph_us"] = 1e3 * timed(lambda: tr1.step(x1), 100, warm=5)
+    x3, cb3 = data(4096, 123), codebook(512, (32, 32), 256)
+    w3 = cb3.codebook.weight.data
+    g3 = ops.geometry(x3.shape, (32, 32))
+    out["C3_bmu_ms"] = timed(lambda: ops.bmu(x3, g3, w3, ops.prepare_codebook(w3)), 20)
+    tr3 = somcb.SomTrainer(cb3, lr=1e-4, neighbourhood_step=10 ** 9)
+    out["C3_step_ms"] = timed(lambda: tr3.step(x3), 20)
+    del x3, tr3, cb3
+    x5, cb5 = data(65536, 123), codebook(32768, (8, 8), 16384)
+    w5 = cb5.codebook.weight.data
+    g5 = ops.geometry(x5.shape, (8, 8))
+    cn5 = ops.prepare_codebook(w5)
+    out["C5_shard_bmu_ms"] = timed(lambda: ops.bmu(x5, g5, w5, cn5), 3, warm=1)
+    out["shapes"] = ("C1: 512 patches D=64 K=1024; C3: 4096 patches D=4096 K=512; "
+                     "C5: 1 048 576 patches D=256, 32 768 of 262 144 units")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +388,13 @@ def main():
             extra = _extra_training(dev, world, rank, None)
         except Exception as e:  # noqa: BLE001
             extra = {"error": repr(e)}
+
+    if extra is not None and world == 1 and not args.no_extra:
+        try:
+            torch.cuda.empty_cache()
+            extra["other_configs"] = _extra_configs(dev)
+        except Exception as e:  # noqa: BLE001
+            extra["other_configs"] = {"error": repr(e)}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
