@@ -225,3 +225,46 @@ def test_tokenize_pair_matches_reference_golden():
             assert li is None
         else:
             assert torch.equal(li.cpu(), rec[f"lr_input_{tag}"])
+
+
+@pytest.mark.parametrize("shape", [
+    # (fmaps, C, H, W, pH, pW, K)            tensor-core mode exercised
+    (33, 4, 32, 32, 2, 2, 1000),             # config S, ragged patch / unit tiles
+    (21, 4, 32, 32, 4, 4, 700),              # resident-A
+    (9, 4, 32, 32, 8, 8, 300),               # streamed (TMA-fed A, pre-pass workspace)
+    (50, 4, 32, 32, 32, 32, 515),            # split-K (partial-distance workspace)
+    (48, 3, 12, 18, 2, 3, 333),              # D = 18: scalar builder path
+])
+def test_bmu_writes_stay_inside_their_buffers(shape):
+    """No sanitizer on this pool: call the C-ABI with every output and the workspace embedded in larger
+    sentinel-filled buffers and check the guard bands afterwards (both variants)."""
+    n, c, h, w, ph, pw, k = shape
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(k)
+    x = torch.tanh(torch.randn(n, c, h, w, generator=g)).to(DEV)
+    d = c * ph * pw
+    wgt = torch.tanh(torch.randn(k, d, generator=g)).to(DEV)
+    cn = ops.prepare_codebook(wgt)
+    n_p = n * (h // ph) * (w // pw)
+    guard = 4096
+    st = torch.cuda.current_stream().cuda_stream
+    for variant in (ops.SOM_BMU_FFMA, ops.SOM_BMU_TC3X):
+        ws_bytes = lib.som_bmu_workspace_bytes(n_p, d, k, variant)
+        ws_big = torch.full((ws_bytes + 2 * guard + 256,), 0x5A, dtype=torch.uint8, device=DEV)
+        base = ws_big.data_ptr() + guard
+        ws_ptr = (base + 255) // 256 * 256
+        off = ws_ptr - ws_big.data_ptr()
+        idx_big = torch.full((n_p + 2 * 512,), -777, dtype=torch.int64, device=DEV)
+        rd_big = torch.full((n_p + 2 * 512,), -777.0, dtype=torch.float32, device=DEV)
+        rc = lib.som_bmu_nchw_f32(x.data_ptr(), n, c, h, w, ph, pw, wgt.data_ptr(), cn.data_ptr(), k, 0,
+                                  idx_big.data_ptr() + 512 * 8, rd_big.data_ptr() + 512 * 4,
+                                  ws_ptr if ws_bytes else None, ws_bytes, variant, st)
+        assert rc == 0, lib.som_last_error()
+        torch.cuda.synchronize()
+        assert bool((idx_big[:512] == -777).all()) and bool((idx_big[512 + n_p:] == -777).all())
+        assert bool((rd_big[:512] == -777.0).all()) and bool((rd_big[512 + n_p:] == -777.0).all())
+        assert bool((ws_big[:off] == 0x5A).all()) and bool((ws_big[off + ws_bytes:] == 0x5A).all())
+        got = idx_big[512:512 + n_p]
+        assert int(got.min()) >= 0 and int(got.max()) < k
+        ref = ops.bmu(x, ops.geometry(x.shape, (ph, pw)), wgt, cn, variant=ops.SOM_BMU_FFMA)
+        assert int((got != ref).sum()) <= max(1, n_p // 2000)          # near-ties only
