@@ -88,21 +88,31 @@ filter_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int 
 }
 
 // Tiled variant (D % 4 == 0, D >= 48, 16-byte aligned rows).  The scalar kernel above waits a full L2 round trip
-// per group of TA rows; here a CTA owns 64 units x 64 features, streams the input rows it needs through shared
-// memory in coalesced 64-row chunks, and every thread keeps a 4 x 4 register tile: 4 LDS.128 + 7 table reads
-// per 64 FFMAs.  Same summation order per output as the scalar kernel (ascending j; rows outside a unit's band
-// meet an exactly-zero weight).
-constexpr int FT_TK = 64, FT_TD = 64, FT_JC = 64, FT_THREADS = 256;
-constexpr int FT_PAD = FT_TK + FT_JC + 8;
+// per group of TA rows; here a CTA owns 32 units x TD features (TD = 128, or 64 for short rows), streams the
+// input rows it needs through shared memory in coalesced, double-buffered (cp.async) 64-row chunks, and every
+// thread keeps an 8-unit x 4-feature register tile (8 LDS.128 + 15 table reads per 256 FFMAs; a 4 x 4 tile is
+// shared-memory-port bound).  There are only K*D/32 such tiles -- 1.7 warps per scheduler at C4 -- so the rows of
+// every chunk are split over JS threads per tile (JS = 4 for TD = 64, 2 for TD = 128) and the JS partial sums are
+// added in fixed order through shared memory at the end: deterministic, fp32 association differs from the scalar
+// kernel by the split only.
+constexpr int FT_JC = 64, FT_THREADS = 256, FT_U = 8;
+constexpr int FT_PAD = 128 + FT_JC + 8;          // covers the unit tile + one chunk of overshoot
 
+template <int TD, int JS>
 __global__ void __launch_bounds__(FT_THREADS)
 filter_tile_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int D,
                    float two_var, int h, float scale) {
+    constexpr int FG = TD / 4;                     // feature groups (threads) per row
+    constexpr int UG = FT_THREADS / (FG * JS);     // unit groups per CTA
+    constexpr int FT_TK = UG * FT_U;               // units per CTA (32)
+    constexpr int CHUNK4 = FT_JC * FG;             // float4 per chunk buffer
+    constexpr int ROWS = FT_JC / JS;               // rows of a chunk per split
+    static_assert(ROWS % FT_U == 0 && (JS - 1) * UG * FG * FT_U <= 2 * CHUNK4, "tile shape");
     extern __shared__ float fsm[];
     const int off = h + FT_PAD;
     const int tab_n = 2 * off + 1;
     float* tab = fsm;
-    float4* chunk = reinterpret_cast<float4*>(fsm + ((tab_n + 3) & ~3));         // [FT_JC][FT_TD / 4]
+    float4* chunk = reinterpret_cast<float4*>(fsm + ((tab_n + 3) & ~3));         // [2][FT_JC][FG]
     for (int i = threadIdx.x; i < tab_n; i += FT_THREADS) {
         int t = i - off;
         int at = t < 0 ? -t : t;
@@ -114,40 +124,58 @@ filter_tile_kernel(const float* __restrict__ in, float* __restrict__ out, int K,
         tab[i] = w;
     }
     const int a_tile = blockIdx.x * FT_TK;
-    const int d_tile = blockIdx.y * FT_TD;
-    const int ug = threadIdx.x >> 4, fg = threadIdx.x & 15;
-    const int a0 = a_tile + 4 * ug;
+    const int d_tile = blockIdx.y * TD;
+    const int js = threadIdx.x / (UG * FG);
+    const int tile = threadIdx.x % (UG * FG);
+    const int ug = tile / FG, fg = tile % FG;
+    const int a0 = a_tile + FT_U * ug;
     int j_lo = a_tile - h; if (j_lo < 0) j_lo = 0;
     int j_hi = a_tile + FT_TK - 1 + h; if (j_hi > K - 1) j_hi = K - 1;
 
-    float4 acc[4];
+    float4 acc[FT_U];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < FT_U; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int jc = j_lo; jc <= j_hi; jc += FT_JC) {
-        __syncthreads();                                    // table ready / previous chunk consumed
+    // chunks are double-buffered: cp.async brings chunk c + 1 in while chunk c is being multiplied
+    auto issue = [&](int jc, int buf) {
 #pragma unroll
-        for (int i = 0; i < FT_JC * (FT_TD / 4) / FT_THREADS; ++i) {
+        for (int i = 0; i < CHUNK4 / FT_THREADS; ++i) {
             const int idx = threadIdx.x + FT_THREADS * i;
-            const int r = idx >> 4, c4 = idx & 15;
+            const int r = idx / FG, c4 = idx % FG;
             const int j = jc + r, d = d_tile + 4 * c4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j <= j_hi && d < D) v = __ldg(reinterpret_cast<const float4*>(in + (int64_t)j * D + d));
-            chunk[idx] = v;
+            float4* dst = chunk + buf * CHUNK4 + idx;
+            if (j <= j_hi && d < D) {
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(in + (int64_t)j * D + d) : "memory");
+            } else {
+                *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        __syncthreads();
-#pragma unroll 4
-        for (int r = 0; r < FT_JC; r += 4) {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(j_lo, 0);
+    int it = 0;
+    for (int jc = j_lo; jc <= j_hi; jc += FT_JC, ++it) {
+        const int buf = it & 1;
+        const bool more = jc + FT_JC <= j_hi;
+        if (more) issue(jc + FT_JC, buf ^ 1);              // the other buffer was released by the sync below
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                    // table + chunk `buf` visible to every thread
+        const float4* cur = chunk + buf * CHUNK4;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; rr += FT_U) {
+            const int r = js * ROWS + rr;
             const int t0 = (jc + r) - a0 + off;             // weight index of (row jc + r, unit a0)
-            float wv[7];
+            float wv[2 * FT_U - 1];
 #pragma unroll
-            for (int q = 0; q < 7; ++q) wv[q] = tab[t0 - 3 + q];
+            for (int q = 0; q < 2 * FT_U - 1; ++q) wv[q] = tab[t0 - (FT_U - 1) + q];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 v = chunk[(r + u) * (FT_TD / 4) + fg];
+            for (int u = 0; u < FT_U; ++u) {
+                const float4 v = cur[(r + u) * FG + fg];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float w = wv[u - i + 3];          // w(|(jc + r + u) - (a0 + i)|)
+                for (int i = 0; i < FT_U; ++i) {
+                    const float w = wv[u - i + FT_U - 1];   // w(|(jc + r + u) - (a0 + i)|)
                     acc[i].x = fmaf(w, v.x, acc[i].x);
                     acc[i].y = fmaf(w, v.y, acc[i].y);
                     acc[i].z = fmaf(w, v.z, acc[i].z);
@@ -155,14 +183,29 @@ filter_tile_kernel(const float* __restrict__ in, float* __restrict__ out, int K,
                 }
             }
         }
+        __syncthreads();                                    // chunk `buf` consumed before it is refilled
     }
-    const int d = d_tile + 4 * fg;
-    if (d < D) {
+    // fixed-order sum of the JS row-split partials (the chunk buffers are free now)
+    float4* red = chunk;
+    if (js > 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < FT_U; ++i) red[((js - 1) * UG * FG + tile) * FT_U + i] = acc[i];
+    }
+    __syncthreads();
+    const int d = d_tile + 4 * fg;
+    if (js == 0 && d < D) {
+#pragma unroll
+        for (int i = 0; i < FT_U; ++i) {
+            float4 t = acc[i];
+#pragma unroll
+            for (int q = 1; q < JS; ++q) {
+                const float4 p = red[((q - 1) * UG * FG + tile) * FT_U + i];
+                t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w;
+            }
             if (a0 + i < K)
                 *reinterpret_cast<float4*>(out + (int64_t)(a0 + i) * D + d) =
-                    make_float4(scale * acc[i].x, scale * acc[i].y, scale * acc[i].z, scale * acc[i].w);
+                    make_float4(scale * t.x, scale * t.y, scale * t.z, scale * t.w);
+        }
     }
 }
 
@@ -206,18 +249,22 @@ extern "C" int som_filter_f32(const float* in, float* out, int K, int D,
         attr_set = true;
     }
     if ((D & 3) == 0 && D >= 48 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+        const int td = D >= 128 ? 128 : 64;
         const size_t tab_n = (size_t)(2 * (h + FT_PAD) + 1);
-        const size_t smem_t = ((tab_n + 3) & ~(size_t)3) * sizeof(float) + (size_t)FT_JC * FT_TD * sizeof(float);
+        const size_t smem_t = ((tab_n + 3) & ~(size_t)3) * sizeof(float) + 2 * (size_t)FT_JC * td * sizeof(float);
         SOM_REQUIRE(smem_t <= 200 * 1024, SOM_E_SHAPE, "filter: band half-width %d too large", h);
         static bool attr_t = false;
-        if (smem_t > 48 * 1024 && !attr_t) {
-            cudaError_t e = cudaFuncSetAttribute(filter_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (!attr_t) {
+            cudaError_t e = cudaFuncSetAttribute(filter_tile_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  200 * 1024);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(filter_tile_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) { set_error("filter: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
             attr_t = true;
         }
-        dim3 gt((unsigned)ceil_div64(K, FT_TK), (unsigned)ceil_div64(D, FT_TD));
-        filter_tile_kernel<<<gt, FT_THREADS, smem_t, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);
+        dim3 gt((unsigned)ceil_div64(K, 32), (unsigned)ceil_div64(D, td));      // 32 units per CTA in both shapes
+        if (td == 128) filter_tile_kernel<128, 2><<<gt, FT_THREADS, smem_t, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);
+        else filter_tile_kernel<64, 4><<<gt, FT_THREADS, smem_t, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);
         return check_launch("filter_tile_kernel");
     }
     dim3 grid((unsigned)ceil_div64(K, FILT_WARPS * FILT_TA), (unsigned)ceil_div64(D, 32));
