@@ -110,6 +110,22 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def _trained_like_codebook(k, patch, seed=7):
+    """Seeded synthetic codebook for OUR arm: K distinct data patches drawn from an independent pool of
+    tanh(randn) fmaps.  Same recipe as the oracle's helper, restated here so that the measured
+    arm imports nothing from oracle/."""
+    import somcb
+    p_h, p_w = patch
+    seq = (32 // p_h) * (32 // p_w)
+    n_fmaps = max(2, (2 * k + seq - 1) // seq)
+    g = torch.Generator().manual_seed(1000 + seed)
+    pool = somcb.patchify(torch.tanh(torch.randn(n_fmaps, 4, 32, 32, generator=g)), patch)
+    pool = pool.reshape(-1, pool.shape[-1])
+    g2 = torch.Generator().manual_seed(int(seed))
+    pick = torch.randperm(pool.shape[0], generator=g2)[:k]
+    return pool[pick].clone().contiguous()
+
+
 def _c2_inputs(dev, seed):
     g = torch.Generator(device=dev).manual_seed(seed)
     x = torch.empty(C2["n_fmaps"], C2["C"], C2["H"], C2["W"], device=dev)
@@ -121,8 +137,7 @@ def _c2_inputs(dev, seed):
 
 def _c2_codebook(dev=None):
     import somcb
-    from oracle.step_oracle import trained_like_codebook   # seeded synthetic weights only
-    w = trained_like_codebook(C2["K"], C2["patch"], 7)
+    w = _trained_like_codebook(C2["K"], C2["patch"], 7)
     cb = somcb.Codebook(patch_dim=C2["patch"], image_dim=(C2["H"], C2["W"]), image_channel=C2["C"],
                         num_embeddings=C2["K"], init_neighbour_range=C2["K"] // 2)
     with torch.no_grad():
@@ -170,14 +185,13 @@ def run_reference(args):
 def _extra_training(dev, world, rank, group):
     """BMU + update step (BASELINE config 4 shape: P=4 D=64 K=16384, 2^20 patches per GPU per step)."""
     import somcb
-    from oracle.step_oracle import trained_like_codebook
     k, pd, n_f = 16384, (4, 4), 16384
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     x = torch.tanh(torch.randn(n_f, 4, 32, 32, generator=g, device=dev))
     cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
                         init_neighbour_range=k // 2)
     with torch.no_grad():
-        cb.codebook.weight.copy_(trained_like_codebook(k, pd, 7))
+        cb.codebook.weight.copy_(_trained_like_codebook(k, pd, 7))
     cb = cb.to(dev)
     tr = somcb.DataParallelSom(cb, lr=1e-4, neighbourhood_step=200) if world > 1 else \
         somcb.SomTrainer(cb, lr=1e-4, neighbourhood_step=200)

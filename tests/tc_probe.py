@@ -1,5 +1,5 @@
 """Probe one BMU shape on the GPU with a chosen variant: parity vs the CPU oracle + timing.
-usage: python tools/tc_probe.py <fmaps> <pH> <K> <variant> [fresh]   (4x32x32 fmaps)"""
+usage: python tests/tc_probe.py <fmaps> <pH> <K> <variant> [fresh]   (4x32x32 fmaps)"""
 import os
 import sys
 import time

@@ -207,7 +207,7 @@ def test_alternate_tensor_core_paths_in_a_subprocess(env):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    probe = os.path.join(root, "tools", "tc_probe.py")
+    probe = os.path.join(root, "tests", "tc_probe.py")
     shapes = [("16", "8", "2048"), ("40", "4", "1000"), ("3", "8", "777"), ("64", "32", "512"), ("700", "4", "600")]
     for shp in shapes:
         r = subprocess.run([sys.executable, probe, *shp, "2"], env={**os.environ, **env},
