@@ -254,13 +254,13 @@ def _extra_configs(dev):
 
     out = {}
     x1, cb1 = data(8, 123), codebook(1024, (4, 4), 512)
-    tr1 = somcb.SomTrainer(cb1, lr=1e-4, neighbourhood_step=10 ** 9, use_cuda_graph=True)
+    tr1 = somcb.SomTrainer(cb1, lr=1e-4, neighbourhood_step=10 ** 9, use_cuda_graph="alias")
     out["C1_step_cuda_graph_us"] = 1e3 * timed(lambda: tr1.step(x1), 100, warm=5)
     x3, cb3 = data(4096, 123), codebook(512, (32, 32), 256)
     w3 = cb3.codebook.weight.data
     g3 = ops.geometry(x3.shape, (32, 32))
     out["C3_bmu_ms"] = timed(lambda: ops.bmu(x3, g3, w3, ops.prepare_codebook(w3)), 20)
-    tr3 = somcb.SomTrainer(cb3, lr=1e-4, neighbourhood_step=10 ** 9)
+    tr3 = somcb.SomTrainer(cb3, lr=1e-4, neighbourhood_step=10 ** 9, use_cuda_graph="alias")
     out["C3_step_ms"] = timed(lambda: tr3.step(x3), 20)
     del x3, tr3, cb3
     x5, cb5 = data(65536, 123), codebook(32768, (8, 8), 16384)

@@ -31,8 +31,10 @@ class SomTrainer:
         ~10 launches of a step, not by the kernels.  With this flag the step is captured once per
         (batch shape, neighbourhood range, lr) into a CUDA graph and replayed: the batch is copied
         into a static buffer, Adam's step count lives in device memory (``som_adam_devstep_f32``).
-        Single-device only; the first step always runs eagerly (it performs the one-time kernel
-        attribute set-up that must not happen during capture)."""
+        ``use_cuda_graph="alias"`` captures on the caller's own input buffer instead of copying into a
+        static one: for loops that refill ONE device staging buffer every step (a changed address forces a
+        re-capture).  Single-device only; the first step always runs eagerly (it performs the one-time
+        kernel attribute set-up that must not happen during capture)."""
         self.cb = codebook
         self.lr = float(lr)
         self.neighbourhood_step = int(neighbourhood_step)
@@ -50,6 +52,7 @@ class SomTrainer:
         self.t = 0
         self.last_bmu = None
         self.use_cuda_graph = bool(use_cuda_graph) and reduce_fn is None
+        self._graph_alias = use_cuda_graph == "alias"
         self._graph = None            # (key, CUDAGraph, x_static, loss_static, t_dev)
 
     @torch.no_grad()
@@ -62,9 +65,12 @@ class SomTrainer:
 
     def _graph_step(self, feature_map):
         cb = self.cb
-        key = (tuple(feature_map.shape), float(cb.neighbourhood_range), float(self.lr))
+        alias = self._graph_alias and feature_map.is_contiguous() and feature_map.dtype == torch.float32
+        key = (tuple(feature_map.shape), float(cb.neighbourhood_range), float(self.lr),
+               feature_map.data_ptr() if alias else 0)
         if self._graph is None or self._graph[0] != key:
-            x_static = torch.empty(feature_map.shape, dtype=torch.float32, device=feature_map.device)
+            x_static = feature_map if alias else \
+                torch.empty(feature_map.shape, dtype=torch.float32, device=feature_map.device)
             t_dev = torch.full((1,), self.t, dtype=torch.int64, device=feature_map.device)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(feature_map.device)
@@ -72,7 +78,8 @@ class SomTrainer:
                 loss_static = self._eager_step(x_static, None, t_dev=t_dev, bookkeeping=False)
             self._graph = (key, graph, x_static, loss_static, t_dev)
         _, graph, x_static, loss_static, t_dev = self._graph
-        x_static.copy_(feature_map)
+        if x_static is not feature_map:
+            x_static.copy_(feature_map)
         graph.replay()
         self.t += 1
         cb._norm_cache = None

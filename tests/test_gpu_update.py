@@ -206,19 +206,25 @@ def test_cuda_graph_trainer_matches_eager_trainer():
     pd, k = (4, 4), 1024
     w0 = trained_like_codebook(k, pd, 7)
     trainers = []
-    for graph in (False, True):
+    for graph in (False, True, "alias"):
         cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
                             init_neighbour_range=k // 2)
         with torch.no_grad():
             cb.codebook.weight.copy_(w0)
         cb = cb.to(DEV)
         trainers.append(somcb.SomTrainer(cb, lr=1e-4, neighbourhood_step=20, use_cuda_graph=graph))
+    staging = torch.empty(8, 4, 32, 32, device=DEV)        # the "alias" trainer replays on this buffer
     for step in range(60):
         x = synthetic_fmaps(8, 123 + step).to(DEV)
+        staging.copy_(x)
         l0 = float(trainers[0].step(x))
         l1 = float(trainers[1].step(x))
+        l2 = float(trainers[2].step(staging))
         assert abs(l0 - l1) <= 1e-6 * abs(l0), f"step {step}: loss {l0} vs {l1}"
-    assert trainers[1]._graph is not None and trainers[1].t == 60
-    assert trainers[0].cb.neighbourhood_range == trainers[1].cb.neighbourhood_range == k // 2 - 3
-    assert_close_norm(trainers[1].cb.codebook.weight.data, trainers[0].cb.codebook.weight.data,
-                      what="weights after 60 graph-replayed steps")
+        assert abs(l0 - l2) <= 1e-6 * abs(l0), f"step {step}: loss {l0} vs {l2} (alias)"
+    for tr in trainers[1:]:
+        assert tr._graph is not None and tr.t == 60
+        assert trainers[0].cb.neighbourhood_range == tr.cb.neighbourhood_range == k // 2 - 3
+        assert_close_norm(tr.cb.codebook.weight.data, trainers[0].cb.codebook.weight.data,
+                          what="weights after 60 graph-replayed steps")
+    assert trainers[2]._graph[2] is staging
