@@ -75,6 +75,14 @@ SOM_API int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd
                      int64_t* out_idx, float* out_rd,
                      void* ws, size_t ws_bytes, int variant, void* stream);
 
+/* Same search on pre-flattened patch rows: `patches` is (n, D) row-major fp32 (what patchify +
+ * reshape produce in models/Codebook.py:83-84).  Equivalent to som_bmu_nchw_f32 with the rows seen
+ * as n one-patch images (n_img = n, C = 1, H = 1, W = D, pH = 1, pW = D).                       */
+SOM_API int som_bmu_flat_f32(const float* patches, int64_t n, int D,
+                     const float* W, const float* c_norm2, int K, int64_t unit_offset,
+                     int64_t* out_idx, float* out_rd,
+                     void* ws, size_t ws_bytes, int variant, void* stream);
+
 /* ---- K1b: merge per-shard candidates (new; multi-GPU unit-sharded search) ---------------
  * rd, idx are (R, n) row-major; picks the smaller rd, ties -> the smaller global index,
  * which reproduces the single-device first-minimum rule when shards are index-ordered.   */
@@ -105,6 +113,13 @@ SOM_API int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int H,
                             const int64_t* bmu, const float* Wt, int K,
                             float* Rbar, int64_t* counts, double* sse,
                             void* ws, size_t ws_bytes, void* stream);
+
+/* Autograd backward of the quantise gather (drop-in path): Rbar[a] = sum_{p: bmu[p]==a} patchify(grad_out)[p]
+ * -- the segment sum the reference's S^T @ grad reduces to after S = onehot(bmu) @ T; follow it
+ * with som_filter_f32(scale = 1) to obtain grad_W (autograd of models/Codebook.py:128-130).
+ * Same workspace as som_accumulate_nchw_f32 (this is that kernel with Wt = NULL).             */
+SOM_API int som_backward_nchw_f32(const float* grad_out, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                          const int64_t* bmu, int K, float* Rbar, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- quantise: gather rows by BMU, fused unpatchify -------------------------------------
  * out[n, c, ph*pH+i, pw*pW+j] = table[idx[n*Seq+s]][d].  With table = T@W this is the

@@ -491,3 +491,10 @@ extern "C" int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int
     if (vec == 2) return launch_levels<2>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
     return launch_levels<1>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
 }
+
+extern "C" int som_backward_nchw_f32(const float* grad_out, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                                     const int64_t* bmu, int K, float* Rbar, void* ws, size_t ws_bytes,
+                                     void* stream) {
+    return som_accumulate_nchw_f32(grad_out, n_img, C, H, Wd, pH, pW, bmu, nullptr, K, Rbar, nullptr, nullptr, ws,
+                                   ws_bytes, stream);
+}

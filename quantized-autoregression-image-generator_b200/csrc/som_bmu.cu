@@ -52,3 +52,11 @@ extern "C" int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int
     return launch_bmu_ffma(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes,
                            (cudaStream_t)stream);
 }
+
+extern "C" int som_bmu_flat_f32(const float* patches, int64_t n, int D, const float* W, const float* c_norm2, int K,
+                                int64_t unit_offset, int64_t* out_idx, float* out_rd,
+                                void* ws, size_t ws_bytes, int variant, void* stream) {
+    SOM_REQUIRE(D > 0, SOM_E_BADARG, "bmu(flat): D=%d", D);
+    return som_bmu_nchw_f32(patches, n, 1, 1, D, 1, D, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes,
+                            variant, stream);
+}

@@ -24,6 +24,10 @@ SIGNATURES = {
     "som_bmu_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_int, c_void_p]),
+    "som_bmu_flat_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
+                                 c_void_p, c_size_t, c_int, c_void_p]),
+    "som_backward_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "som_merge_candidates": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "som_histogram_i64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "som_filter_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p]),

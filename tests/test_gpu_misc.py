@@ -268,3 +268,30 @@ def test_bmu_writes_stay_inside_their_buffers(shape):
         assert int(got.min()) >= 0 and int(got.max()) < k
         ref = ops.bmu(x, ops.geometry(x.shape, (ph, pw)), wgt, cn, variant=ops.SOM_BMU_FFMA)
         assert int((got != ref).sum()) <= max(1, n_p // 2000)          # near-ties only
+
+
+def test_flat_and_backward_entry_points_match_their_general_forms():
+    """som_bmu_flat_f32 == BMU over patchified rows; som_backward_nchw_f32 == accumulate with Wt = NULL."""
+    lib = _lib.load()
+    x = synthetic_fmaps(12, 5).to(DEV)
+    pd, k = (4, 4), 600
+    wgt = trained_like_codebook(k, pd, 3).to(DEV)
+    cn = ops.prepare_codebook(wgt)
+    geom = ops.geometry(x.shape, pd)
+    ref = ops.bmu(x, geom, wgt, cn, variant=ops.SOM_BMU_FFMA)
+    flat = somcb.patchify(x, pd).reshape(-1, 64).contiguous()
+    n_p = flat.shape[0]
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.empty(n_p, dtype=torch.int64, device=DEV)
+    nb = lib.som_bmu_workspace_bytes(n_p, 64, k, ops.SOM_BMU_FFMA)
+    ws = torch.empty(max(nb, 1), dtype=torch.uint8, device=DEV)
+    rc = lib.som_bmu_flat_f32(flat.data_ptr(), n_p, 64, wgt.data_ptr(), cn.data_ptr(), k, 0, out.data_ptr(), None,
+                              ws.data_ptr(), nb, ops.SOM_BMU_FFMA, st)
+    assert rc == 0 and torch.equal(out, ref)
+    g_out = torch.randn_like(x)
+    want, _, _ = ops.accumulate(g_out, geom, ref, None, k)
+    rbar = torch.empty(k, 64, device=DEV)
+    nb2 = lib.som_accumulate_workspace_bytes(n_p, 64, k)
+    ws2 = torch.empty(nb2, dtype=torch.uint8, device=DEV)
+    rc = lib.som_backward_nchw_f32(g_out.data_ptr(), *geom, ref.data_ptr(), k, rbar.data_ptr(), ws2.data_ptr(), nb2, st)
+    assert rc == 0 and torch.equal(rbar, want)
