@@ -381,6 +381,12 @@ def main():
     # nominal fp32-faithful roof of this shape: 2048 TF32 MAC/clk/SM x 148 SMs x max clock / 3 products,
     # times the useful fraction of the K' = 3*16 + 8 inner dimension
     nominal = 2048 * 2 * 148 * 1.965e9 / 3.0 * (48.0 / 56.0) / 1e12
+    # the tensor pipe's own sustained TF32 rate on this pool (tools/mma_rate.cu, power-capped clock), / 3 products
+    pipe_peak = None
+    ppath = os.path.join(ROOT, "profiles", "measured_pipe_peaks.json")
+    if os.path.exists(ppath):
+        with open(ppath) as f:
+            pipe_peak = json.load(f).get("tf32_3x_fp32_faithful_tflops_sustained")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                 "frac": achieved / tc_peak, "traffic": traffic,
                 "kernel": "bmu_tc3x (tcgen05 kind::tf32 x3)" if variant == 2 else "bmu_ffma (fp32 FFMA)",
@@ -390,10 +396,14 @@ def main():
                 "hbm_frac": (4 * d_dim + 8) * n_p / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "ffma_frac_of_derived_74.4TF": achieved / FFMA_PEAK_TFLOPS,
                 "frac_of_nominal_tf32_pipe": achieved / nominal,
+                "frac_of_measured_tcgen05_tf32_peak": (achieved / pipe_peak) if pipe_peak else None,
+                "measured_tcgen05_tf32_peak_3x": pipe_peak,
                 "tensor_pipe_active_pct_ncu": pipe_pct,
                 "note": "frac > 1 is expected: the denominator is the measured sustained cuBLAS bf16 rate / 6; "
                         "the kernel keeps the tensor pipe ~94% active (ncu) and is bounded by the SM clock "
-                        "under the power cap (1.55-1.65 GHz)"}
+                        "under the power cap (1.55-1.65 GHz).  Against the tensor pipe's own measured sustained "
+                        "TF32 rate (930 TFLOP/s dense = 310 fp32-faithful) see frac_of_measured_tcgen05_tf32_peak; "
+                        "7 MMAs per tile carry 6 MMAs of useful products (K' = 56 for 3*16)"}
 
     extra = None
     if not args.no_extra:

@@ -491,7 +491,75 @@ static void run(const char* name, int kblocks) {
     cudaFree(out); cudaFree(fb); cudaFree(src);
 }
 
-int main() {
+
+// ---- sustained peaks: a long tcgen05 TF32 run (power-capped clock) and an FP32 FFMA run, timed with events ----
+__global__ void __launch_bounds__(1024) ffma_peak_kernel(float* out, int iters) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-6f + i;
+    const float b = 1.000001f, c = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123.456f) out[threadIdx.x] = s;
+}
+
+static void run_sustained() {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    // TF32 tensor pipe: ~0.6 s of back-to-back M128 N256 K8 MMAs on every SM
+    {
+        const int grid = 148, kblocks = 2, iters = 600000;     // 4.8 M MMAs per CTA
+        long long* out; long long* fb; uint8_t* src;
+        cudaMalloc(&out, grid * sizeof(long long)); cudaMalloc(&fb, grid * sizeof(long long)); cudaMalloc(&src, 8 * 131072);
+        const int smem = 1024 + kblocks * (128 * 128 + 256 * 128) + 32768;
+        cudaFuncSetAttribute(rate_kernel<1, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, rate_kernel<1, 256, 32>, 1000, kblocks, out, (const uint8_t*)src, fb);
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        cudaLaunchKernelEx(&cfg, rate_kernel<1, 256, 32>, iters, kblocks, out, (const uint8_t*)src, fb);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        const double n_mma = (double)iters * kblocks * 4;
+        const double tf = 148.0 * n_mma * 128 * 256 * 8 * 2 / (ms * 1e-3) / 1e12;
+        printf("SUSTAINED tf32 tcgen05 (random operands): %.1f ms, %.1f TFLOP/s dense TF32 -> %.1f TFLOP/s fp32-faithful (3 products), "
+               "%.1f cycles/MMA, average SM clock %.3f GHz  [%s]\n", ms, tf, tf / 3.0, (double)h[0] / n_mma,
+               (double)h[0] / (ms * 1e-3) / 1e9, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+        cudaFree(out); cudaFree(fb); cudaFree(src);
+    }
+    // FP32 FFMA: 148 x 2 CTAs x 1024 threads, 64 independent FMAs per iteration
+    {
+        float* out; cudaMalloc(&out, 4096);
+        const int iters = 200000;
+        ffma_peak_kernel<<<148 * 2, 1024>>>(out, 1000);
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        ffma_peak_kernel<<<148 * 2, 1024>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 148.0 * 2 * 1024 * (double)iters * 64 * 2;
+        printf("SUSTAINED fp32 FFMA: %.1f ms, %.1f TFLOP/s\n", ms, fl / (ms * 1e-3) / 1e12);
+        cudaFree(out);
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == 's') { run_sustained(); return 0; }
     run_probe();
     run_probe2(0);
     run_probe2(1);
