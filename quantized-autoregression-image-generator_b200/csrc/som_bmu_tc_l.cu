@@ -1,8 +1,8 @@
-// K1 (tensor-core variant), large patch dimension ("config L": D too large for a resident patch tile):
-// BMU search as an error-compensated 3xTF32 GEMM on tcgen05, both operands streamed.  sm_100a only.
+// K1 (tensor-core variant), patch dimension D > 16: BMU search as an error-compensated 3xTF32 GEMM on tcgen05.
+// sm_100a only.
 //
 // Replaces patchify + torch.cdist + torch.argmin of Codebook.get_patches_bmu
-// (/root/reference/models/Codebook.py:77-99) for coarse patches: BASELINE config 3 (whole-fmap codebook,
+// (/root/reference/models/Codebook.py:77-99): BASELINE config 1 / 4 (D = 64), config 3 (whole-fmap codebook,
 // D = 4096, K = 512, 4096 patches) and config 5 (D = 256, K = 32 768 per GPU).
 //
 //     rd[p][j] = ||c_j||^2 - 2 x_p . c_j = n1+n2+n3 - 2 x_hi.c_hi - 2 x_lo.c_hi - 2 x_hi.c_lo
@@ -11,23 +11,28 @@
 // K=8 MMAs:  A_hi x B_hi,  A_lo x B_hi,  A_hi x B_lo.  The norms enter through one extra K=8 step
 // (A = [1 1 1 0..], B = [n1 n2 n3 0..], 32-byte rows, SWIZZLE_32B).
 //
-// One persistent CTA per SM, 448 threads, warp-specialised:
-//   warp 0      TMA producer: B_hi / B_lo blocks (256 units x 32 features, 32 KB) of the pre-split codebook
-//                             into a 4-stage ring, norm tails into a 2-stage ring
-//   warp 1      MMA issuer  : warp-uniform loop, one elected lane issues M128 x N256 x K8 kind::tf32 into
-//                             two TMEM accumulator stages
-//   warps 2-9   builders    : two groups of four warps alternate feature blocks: a thread reads the 32 features
-//                             of its patch row straight from NCHW (patchify = address arithmetic, the next block's
-//                             loads in flight while the current one is converted), splits hi/lo and writes both
-//                             swizzled 16 KB operand blocks of its A-ring slot -- no pre-pass, no operand copy in HBM
+// One persistent CTA per SM (or CTA pair per two SMs), 448 threads, warp-specialised:
+//   warp 0      TMA producer: B_hi / B_lo blocks of the pre-split codebook into a 128 KB ring, norm tails into a
+//                             2-stage ring; in the streamed mode also the pre-split A blocks
+//   warp 1      MMA issuer  : warp-uniform loop, one elected lane issues M128 (M256 for pairs) x N256 x K8
+//                             kind::tf32 into two TMEM accumulator stages
+//   warps 2-9   builders    : two groups of four warps: a thread reads 32 features of its patch row straight from
+//                             NCHW (patchify = address arithmetic, the next block's loads in flight while the
+//                             current one is converted), splits hi/lo and writes both swizzled 16 KB operand
+//                             blocks of its A slot -- no operand copy in HBM
 //   warps 10-13 epilogue    : tcgen05.ld of their TMEM lane quarter, all 256 columns
-// Two epilogue modes (static rule on the shape):
-//   ARGMIN   enough patch tiles to fill the machine: running exact (min, index) per patch row over all unit
-//            tiles -- the N x K distance matrix never leaves TMEM
-//   SPLIT-K  few patch tiles (config 3: 32 tiles, 2 unit tiles, 128 feature blocks): the feature axis is
-//            split over S CTAs per patch tile, partial distances (S x N x K fp32, 8 MB per split at config 3)
-//            go to a workspace and a small kernel adds them in fixed order and takes the argmin
-// Bound: tensor pipe (TF32 rate / 3); per feature block the CTA moves 64 KB of B and 16 KB of x.
+// Modes (static rule on the shape, see make_plan):
+//   resident-A  D <= 64: the patch tile's blocks stay in the two A slots for all unit tiles (C1, C4)
+//   streamed    D  > 64, at least as many patch tiles as SMs: split_x_l_kernel pre-splits patch rows into an
+//               L2-sized workspace chunk and the producer streams A by TMA (C5); running exact (min, index) per
+//               patch row over all unit tiles -- the N x K distance matrix never leaves TMEM
+//   split-K     D  > 64, few patch tiles (C3: 32 tiles, 2 unit tiles, 128 feature blocks): the feature axis is
+//               split over S CTAs per patch tile, each A-slot fill feeds both TMEM accumulators (two unit
+//               tiles), partial distances (S x N x K fp32) go to a workspace and splitk_argmin_kernel adds
+//               them in fixed order and takes the argmin
+//   CTA pairs   CG = 2 (cta_group::2): each CTA holds its own A tile and HALF of every B block; resident-A and
+//               streamed modes with at least two waves of patch tiles
+// Bound: tensor pipe (TF32 rate / 3): 94.8 % active at C4, 87 % at C5, 58 % at C3 (profiles/).
 #include "som_common.cuh"
 #include "som_tc_ptx.cuh"
 
