@@ -70,7 +70,7 @@ struct Params {
     float* partial;         // [S][n_mtiles * 128][K_pad]   (S > 1)
     const float* x;
     Geom g;
-    int dbg;                // SOM_TC_DEBUG (timing experiments only)
+    int dbg;                // timing-elimination switches, 0 unless built with -DSOM_TC_EXPERIMENTS
     int a_tma;              // streamed mode: A blocks arrive by TMA from the pre-split workspace (builders idle)
     int tile0;              // first patch tile of this launch inside the workspace chunk numbering (0)
 };
@@ -719,7 +719,11 @@ int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* 
     P.fb_per_split = pl.fb_per_split; P.K_pad = pl.K_pad; P.rows = n; P.unit_offset = unit_offset;
     P.out_idx = out_idx; P.out_rd = out_rd; P.partial = pl.S > 1 ? Pp : nullptr; P.x = x; P.g = g;
     P.a_tma = (mode == 2) ? 1 : 0; P.tile0 = 0;
+    P.dbg = 0;
+#ifdef SOM_TC_EXPERIMENTS
+    // timing-elimination switches (skip refine / loads / conversion): results are wrong, experiment builds only
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SOM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
+#endif
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
     static const KernelFn kernels[2][3] = {

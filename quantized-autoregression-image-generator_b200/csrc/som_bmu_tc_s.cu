@@ -61,7 +61,7 @@ struct Params {
     const float* W;
     const float* cn;
     int K;
-    int dbg;
+    int dbg;                // timing-elimination switches, 0 unless built with -DSOM_TC_EXPERIMENTS
 };
 
 struct __align__(8) Barriers {
@@ -490,7 +490,11 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
     P.nks = Dp / 8; P.NT = K_pad / TN; P.n_mtiles = (int)ceil_div64(n, TM); P.rows = n;
     P.unit_offset = unit_offset; P.out_idx = out_idx; P.out_rd = out_rd;
     P.x = x; P.g = g; P.W = W; P.cn = cn; P.K = K;
+    P.dbg = 0;
+#ifdef SOM_TC_EXPERIMENTS
+    // timing-elimination switches (skip refine / loads / conversion): results are wrong, experiment builds only
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SOM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
+#endif
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(bmu_tc_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
