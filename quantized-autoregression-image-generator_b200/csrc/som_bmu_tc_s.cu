@@ -50,6 +50,7 @@ constexpr int TILES_BYTES = R * A_BLK_BYTES + TAIL_A_BYTES + NSTAGE * STAGE_BYTE
 
 struct Params {
     int nks;                // k-steps per product group: Dp / 8
+    int Rr;                 // resident patch tiles per super-tile in THIS launch (1..R): fewer for small batches
     int NT;                 // unit tiles
     int n_mtiles;           // patch tiles
     int64_t rows;           // valid patches
@@ -128,7 +129,8 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
-    const int n_super = (P.n_mtiles + R - 1) / R;
+    const int Rr = P.Rr;
+    const int n_super = (P.n_mtiles + Rr - 1) / Rr;
     const int nks = P.nks;
 
     if (warp == 0) {
@@ -164,7 +166,7 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         uint32_t phase = 0, a_par = 0, j = 0;
         const long long t_begin = clock64();
         for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
-            const int r_eff = min(R, P.n_mtiles - st * R);
+            const int r_eff = min(Rr, P.n_mtiles - st * Rr);
             for (int n = 0; n < P.NT; ++n) {
                 mbar_wait(&bars.full[stage], phase);
                 const uint64_t bd = bdesc0 + (uint32_t)stage * STAGE_UNITS;
@@ -210,10 +212,10 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         const bool w4 = v4 && ((reinterpret_cast<uintptr_t>(P.W) & 15) == 0);
         float xv[R][DMAX];
         auto prefetch = [&](int st_next) {
-            const int r_nxt = (st_next < n_super) ? min(R, P.n_mtiles - st_next * R) : 0;
+            const int r_nxt = (st_next < n_super) ? min(Rr, P.n_mtiles - st_next * Rr) : 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int64_t p = (int64_t)(st_next * R + r) * TM + t;
+                const int64_t p = (int64_t)(st_next * Rr + r) * TM + t;
                 const bool ok = (r < r_nxt) && (p < P.rows);
                 load_row<DMAX>(xv[r], P.x + (ok ? patch_base(P.g, p) : 0), ok, D, vec, aux.foff);
             }
@@ -266,9 +268,9 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         };
         auto refine_super = [&](int st_done, int it_done) {
             mbar_wait_warp<true>(&bars.ref_full[it_done & 1], (uint32_t)(it_done >> 1) & 1u, lane);
-            const int r_done = min(R, P.n_mtiles - st_done * R);
+            const int r_done = min(Rr, P.n_mtiles - st_done * Rr);
             for (int r = 0; r < r_done; ++r) {
-                const int64_t p = (int64_t)(st_done * R + r) * TM + t;
+                const int64_t p = (int64_t)(st_done * Rr + r) * TM + t;
                 if (p < P.rows) refine_row(p, aux.cbase[it_done & 1][r][t]);
             }
         };
@@ -277,7 +279,7 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         uint32_t a_epar = 1;
         int st_prev = -1, it = 0;
         for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
-            const int r_eff = min(R, P.n_mtiles - st * R);
+            const int r_eff = min(Rr, P.n_mtiles - st * Rr);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r < r_eff) {
@@ -332,7 +334,7 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         uint32_t j = 0;
         int it = 0;
         for (int st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
-            const int r_eff = min(R, P.n_mtiles - st * R);
+            const int r_eff = min(Rr, P.n_mtiles - st * Rr);
             float best[R];
             int bidx[R];
 #pragma unroll
@@ -501,7 +503,11 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
         if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    const int n_super = (P.n_mtiles + R - 1) / R;
+    // small batches: fewer resident tiles per CTA so that every SM gets a super-tile (a unit tile then feeds
+    // fewer MMAs, but the sweep over the unit tiles is what bounds a small batch)
+    int rr = (P.n_mtiles + sm_count() - 1) / sm_count();
+    P.Rr = rr < 1 ? 1 : (rr > R ? R : rr);
+    const int n_super = (P.n_mtiles + P.Rr - 1) / P.Rr;
     const int grid = n_super < sm_count() ? n_super : sm_count();
     bmu_tc_s_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
     return check_launch("bmu_tc_s_kernel");
