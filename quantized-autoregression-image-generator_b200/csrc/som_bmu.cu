@@ -24,11 +24,12 @@ extern "C" int som_bmu_pick_variant(int64_t n_patches, int D, int K) {
     //    one patch) while the split-K tensor-core mode spreads the axis over the SMs (60-75 us) -> TC always
     //  * D <= 16: equal to FFMA (~28 us at K = 4096) up to 4096 patches, 1.6-3.4x faster from 8192 on (the kernel
     //    keeps fewer resident tiles per CTA for small batches, so every SM gets a super-tile) -> TC from 4096
-    //  * 17 <= D <= 64 with a small codebook: resident-A TC wins at every batch size (21 vs 26 us at C1)
+    //  * 17 <= D <= 64: resident-A TC wins at every batch size (21 vs 26 us at C1; with many unit tiles and few
+    //    patch tiles the unit tiles are split over CTAs and merged: 33 us vs 48-116 us at K = 16 384, n <= 2048)
     //  * otherwise TC from 4096 patches (a single patch tile would sweep K / 256 unit tiles serially)
     if (!tc_supported(n_patches, D, K) || (int64_t)K * D < 16384) return SOM_BMU_FFMA;
     if (D >= 512) return SOM_BMU_TC3X;
-    if (D <= 64 && K <= 2048) return SOM_BMU_TC3X;
+    if (D > 16 && D <= 64) return SOM_BMU_TC3X;
     return n_patches >= 4096 ? SOM_BMU_TC3X : SOM_BMU_FFMA;
 }
 

@@ -62,6 +62,10 @@ struct Params {
     int n_mtiles;           // patch tiles
     int S;                  // feature splits (1: ARGMIN epilogue)
     int fb_per_split;
+    int U;                  // unit-tile splits (resident-A mode, small batches): candidates merged afterwards
+    int nt_per_u;
+    float* cand_rd;         // [U][rows]   (U > 1)
+    int64_t* cand_idx;      // [U][rows]
     int K_pad;
     int64_t rows;           // valid patches
     int64_t unit_offset;
@@ -163,7 +167,8 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
     // a job = (patch tile [pair], feature split); CTA `rank` of a pair owns patch tile CG * (q / S) + rank
-    const int n_jobs = ((P.n_mtiles + CG - 1) / CG) * P.S;
+    const int SU = P.S * P.U;                       // jobs per patch tile [pair]: feature splits x unit splits
+    const int n_jobs = ((P.n_mtiles + CG - 1) / CG) * SU;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -175,11 +180,12 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             int as = 0;
             uint32_t a_eph = 1;
             for (int q = job0; q < n_jobs; q += job_stride) {
-                const int s = q % P.S;
+                const int s = (q % SU) % P.S, u = (q % SU) / P.S;
                 const int fb0 = s * P.fb_per_split;
                 const int fb1 = min(P.DB, fb0 + P.fb_per_split);
-                for (int n0 = 0; n0 < P.NT; n0 += NI) {
-                    const int ni = min(NI, P.NT - n0);
+                const int nt0 = u * P.nt_per_u, nt1 = min(P.NT, nt0 + P.nt_per_u);
+                for (int n0 = nt0; n0 < nt1; n0 += NI) {
+                    const int ni = min(NI, nt1 - n0);
                     if (s == 0) {
                         for (int a = 0; a < ni; ++a) {
                             const int n = n0 + a;
@@ -193,7 +199,7 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     for (int fb = fb0; fb < fb1; ++fb) {
                         if (P.a_tma) {
                             // pre-split patch rows: hi and lo block of this CTA's tile into A slot `as`
-                            const int m = CG * (q / P.S) + (int)rank;
+                            const int m = CG * (q / SU) + (int)rank;
                             mbar_wait(&bars.a_empty[as], a_eph);
                             if (rank == 0) mbar_expect_tx(&bars.a_full[as], A_SLOT_BYTES * CG);
                             uint8_t* adst = a_ring + (size_t)as * A_SLOT_BYTES;
@@ -242,11 +248,12 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         uint32_t a_ph = 0, b_ph = 0, t_ph = 0, j = 0;
         for (int q = job0; q < n_jobs; q += job_stride) {
             if (ARES && q != job0) a_ph ^= 1;                      // resident slots: one fill per job
-            const int s = q % P.S;
+            const int s = (q % SU) % P.S, u = (q % SU) / P.S;
             const int fb0 = s * P.fb_per_split;
             const int fb1 = min(P.DB, fb0 + P.fb_per_split);
-            for (int n0 = 0; n0 < P.NT; n0 += NI) {
-                const int ni = min(NI, P.NT - n0);
+            const int nt0 = u * P.nt_per_u, nt1 = min(P.NT, nt0 + P.nt_per_u);
+            for (int n0 = nt0; n0 < nt1; n0 += NI) {
+                const int ni = min(NI, nt1 - n0);
                 uint32_t accum[NI];
 #pragma unroll
                 for (int a = 0; a < NI; ++a) {
@@ -274,7 +281,7 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     if (ARES) as = fb;
                     const uint64_t ahi = adesc0 + (uint32_t)as * A_SLOT_UNITS;
                     const uint64_t alo = ahi + A_LO_UNITS;
-                    if (!ARES || n0 == 0) mma_wait(&bars.a_full[as], a_ph);
+                    if (!ARES || n0 == nt0) mma_wait(&bars.a_full[as], a_ph);
 #pragma unroll
                     for (int a = 0; a < NI; ++a) {
                         if (a < ni) {
@@ -305,7 +312,7 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                             if (++bs == NB) { bs = 0; b_ph ^= 1; }
                         }
                     }
-                    if (leader && (!ARES || n0 + ni >= P.NT)) tc_commit_cg<CG>(&bars.a_empty[as]);
+                    if (leader && (!ARES || n0 + ni >= nt1)) tc_commit_cg<CG>(&bars.a_empty[as]);
                     if (!ARES && ++as == NA) { as = 0; a_ph ^= 1; }
                 }
                 if (leader) {
@@ -377,11 +384,11 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         bool ok = false, live = q < n_jobs;
         const float* src = P.x;
         auto enter_job = [&]() {
-            const int s = q % P.S, m = CG * (q / P.S) + (int)rank;
+            const int s = (q % SU) % P.S, m = CG * (q / SU) + (int)rank;
             fb0 = s * P.fb_per_split;
             fb1 = min(P.DB, fb0 + P.fb_per_split);
             fb = fb0;
-            n = 0;
+            n = 0;                           // unit splits (U > 1) exist in resident mode only: n is not used there
             const int64_t p = (int64_t)m * TM + t;
             m_rows0 = (int64_t)m * TM;
             ok = p < P.rows;
@@ -457,11 +464,12 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         const int row = lg * 32 + lane;             // patch row inside the tile
         uint32_t j = 0;
         for (int q = job0; q < n_jobs; q += job_stride) {
-            const int s = q % P.S, m = CG * (q / P.S) + (int)rank;
+            const int s = (q % SU) % P.S, u = (q % SU) / P.S, m = CG * (q / SU) + (int)rank;
+            const int nt0 = u * P.nt_per_u, nt1 = min(P.NT, nt0 + P.nt_per_u);
             const int64_t p = (int64_t)m * TM + row;
             float best = INFINITY;
-            int bidx = 0;
-            for (int n = 0; n < P.NT; ++n) {
+            int bidx = nt0 * TN;
+            for (int n = nt0; n < nt1; ++n) {
                 const uint32_t acc = j & 1u;
                 mbar_wait(&bars.acc_full[acc], (j >> 1) & 1u);
                 tc_fence_after();
@@ -506,8 +514,13 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 ++j;
             }
             if (!SPLITK && p < P.rows) {
-                P.out_idx[p] = (int64_t)bidx + P.unit_offset;
-                if (P.out_rd) P.out_rd[p] = best;
+                if (P.U > 1) {                       // unit split: candidates, merged by merge_kernel
+                    P.cand_idx[(int64_t)u * P.rows + p] = (int64_t)bidx + P.unit_offset;
+                    P.cand_rd[(int64_t)u * P.rows + p] = best;
+                } else {
+                    P.out_idx[p] = (int64_t)bidx + P.unit_offset;
+                    if (P.out_rd) P.out_rd[p] = best;
+                }
             }
         }
     }
@@ -623,9 +636,9 @@ __global__ void __launch_bounds__(256) split_x_l_kernel(const float* __restrict_
 
 struct Plan {
     int cg;
-    int D, K, DB, nks_last, K_pad, NT, n_mtiles, S, fb_per_split;
+    int D, K, DB, nks_last, K_pad, NT, n_mtiles, S, fb_per_split, U, nt_per_u;
     int64_t chunk_rows;            // streamed mode: patches per pre-split workspace chunk (multiple of 128)
-    size_t off_b, off_t, off_p, off_a, total;
+    size_t off_b, off_t, off_p, off_a, off_c, total;
 };
 
 static void make_plan(Plan* pl, int64_t n, int D, int K) {
@@ -643,8 +656,21 @@ static void make_plan(Plan* pl, int64_t n, int D, int K) {
     if (S < 1) S = 1;
     pl->fb_per_split = (pl->DB + S - 1) / S;
     pl->S = (pl->DB + pl->fb_per_split - 1) / pl->fb_per_split;
+    // resident-A mode with few patch tiles and many unit tiles: spread the unit tiles of a patch tile over U
+    // CTAs (each keeps its own copy of the A tile) and merge the U candidates per patch afterwards
+    pl->U = 1;
+    pl->nt_per_u = pl->NT;
+    if (pl->S == 1 && pl->DB <= NA && 2 * pl->n_mtiles <= sm_count() && pl->NT >= 8) {
+        int U = sm_count() / pl->n_mtiles;
+        if (U > pl->NT / 2) U = pl->NT / 2;
+        if (U > 16) U = 16;
+        if (U > 1) {
+            pl->nt_per_u = (pl->NT + U - 1) / U;
+            pl->U = (pl->NT + pl->nt_per_u - 1) / pl->nt_per_u;
+        }
+    }
     pl->cg = 1;
-    if (sm_count() % 2 == 0 && pair_mode() != 0) {
+    if (sm_count() % 2 == 0 && pair_mode() != 0 && pl->U == 1) {
         if (pair_mode() == 1) pl->cg = 2;
         else if (pl->S == 1 && pl->n_mtiles >= 2 * sm_count()) pl->cg = 2;
     }
@@ -668,6 +694,8 @@ static void make_plan(Plan* pl, int64_t n, int D, int K) {
         pl->chunk_rows = chunk;
         o = align_up(o + (size_t)chunk * row_bytes, 1024);
     }
+    pl->off_c = o;
+    if (pl->U > 1) o = align_up(o + (size_t)pl->U * n * (4 + 8), 1024);
     pl->total = o;
 }
 
@@ -717,6 +745,9 @@ int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* 
     Params P;
     P.DB = pl.DB; P.nks_last = pl.nks_last; P.NT = pl.NT; P.n_mtiles = pl.n_mtiles; P.S = pl.S;
     P.fb_per_split = pl.fb_per_split; P.K_pad = pl.K_pad; P.rows = n; P.unit_offset = unit_offset;
+    P.U = pl.U; P.nt_per_u = pl.nt_per_u;
+    P.cand_idx = (int64_t*)((char*)ws + pl.off_c);                      // int64 first: 8-byte aligned
+    P.cand_rd = (float*)((char*)ws + pl.off_c + (size_t)pl.U * n * 8);
     P.out_idx = out_idx; P.out_rd = out_rd; P.partial = pl.S > 1 ? Pp : nullptr; P.x = x; P.g = g;
     P.a_tma = (mode == 2) ? 1 : 0; P.tile0 = 0;
     P.dbg = 0;
@@ -741,7 +772,7 @@ int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* 
         attr_done = true;
     }
     auto launch = [&](const Params& Pl) -> int {
-        const int n_jobs = ((Pl.n_mtiles + pl.cg - 1) / pl.cg) * pl.S;
+        const int n_jobs = ((Pl.n_mtiles + pl.cg - 1) / pl.cg) * pl.S * pl.U;
         const int max_groups = sm_count() / pl.cg;
         const int groups = n_jobs < max_groups ? n_jobs : max_groups;
         cudaLaunchConfig_t cfg = {};
@@ -779,6 +810,8 @@ int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* 
     }
     rc = launch(P);
     if (rc) return rc;
+    if (pl.U > 1)
+        return som_merge_candidates(P.cand_rd, P.cand_idx, pl.U, n, out_idx, out_rd, st);
     if (pl.S > 1) {
         splitk_argmin_kernel<<<(unsigned)ceil_div64(n, 8), 256, 0, st>>>(Pp, pl.S, (int64_t)pl.n_mtiles * TM, pl.K_pad, K,
                                                                        n, unit_offset, out_idx, out_rd);
