@@ -19,17 +19,15 @@ using namespace som;
 
 extern "C" int som_bmu_pick_variant(int64_t n_patches, int D, int K) {
     // Static rule on the shape (no runtime autotuner), from the measured crossovers of tools/crossover.py:
-    //  * tiny codebooks: the tensor-core kernels pay an operand-split pre-pass and 128 x 256 tiles -> FFMA
-    //  * long feature axis (D >= 512): the FFMA kernel walks D in 16-feature slabs (~950 us at D = 4096 even for
-    //    one patch) while the split-K tensor-core mode spreads the axis over the SMs (60-75 us) -> TC always
-    //  * D <= 16: equal to FFMA (~28 us at K = 4096) up to 4096 patches, 1.6-3.4x faster from 8192 on (the kernel
-    //    keeps fewer resident tiles per CTA for small batches, so every SM gets a super-tile) -> TC from 4096
-    //  * 17 <= D <= 64: resident-A TC wins at every batch size (21 vs 26 us at C1; with many unit tiles and few
-    //    patch tiles the unit tiles are split over CTAs and merged: 33 us vs 48-116 us at K = 16 384, n <= 2048)
-    //  * otherwise TC from 4096 patches (a single patch tile would sweep K / 256 unit tiles serially)
+    //  * tiny codebooks (K * D < 16 384): the tensor-core kernels pay an operand-split pre-pass and 128 x 256
+    //    tiles -> FFMA
+    //  * D > 16: TC at every batch size.  Few patch tiles are spread over the SMs by splitting the unit tiles
+    //    (candidates merged afterwards) or, for long feature axes, the features (split-K): 21 vs 26 us at C1,
+    //    33 vs 48-116 us at D = 64 / K = 16 384 / n <= 2048, 30 vs 70 us at D = 256 / K = 2048, 60-75 vs ~950 us at
+    //    D = 4096 (the FFMA kernel walks D in 16-feature slabs)
+    //  * D <= 16: equal to FFMA (~28 us at K = 4096) up to 4096 patches, 1.6-3.4x faster from 8192 on -> TC from 4096
     if (!tc_supported(n_patches, D, K) || (int64_t)K * D < 16384) return SOM_BMU_FFMA;
-    if (D >= 512) return SOM_BMU_TC3X;
-    if (D > 16 && D <= 64) return SOM_BMU_TC3X;
+    if (D > 16) return SOM_BMU_TC3X;
     return n_patches >= 4096 ? SOM_BMU_TC3X : SOM_BMU_FFMA;
 }
 

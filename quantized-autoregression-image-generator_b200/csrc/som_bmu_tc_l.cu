@@ -388,7 +388,7 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             fb0 = s * P.fb_per_split;
             fb1 = min(P.DB, fb0 + P.fb_per_split);
             fb = fb0;
-            n = 0;                           // unit splits (U > 1) exist in resident mode only: n is not used there
+            n = 0;                           // (builders run in the resident and split-K modes; U > 1 excludes split-K)
             const int64_t p = (int64_t)m * TM + t;
             m_rows0 = (int64_t)m * TM;
             ok = p < P.rows;
@@ -657,11 +657,11 @@ static void make_plan(Plan* pl, int64_t n, int D, int K) {
     if (S < 1) S = 1;
     pl->fb_per_split = (pl->DB + S - 1) / S;
     pl->S = (pl->DB + pl->fb_per_split - 1) / pl->fb_per_split;
-    // resident-A mode with few patch tiles and many unit tiles: spread the unit tiles of a patch tile over U
-    // CTAs (each keeps its own copy of the A tile) and merge the U candidates per patch afterwards
+    // few patch tiles and many unit tiles (no feature split): spread the unit tiles of a patch tile over U CTAs
+    // (each builds / streams its own copy of the A tile) and merge the U candidates per patch afterwards
     pl->U = 1;
     pl->nt_per_u = pl->NT;
-    if (pl->S == 1 && pl->DB <= NA && 2 * pl->n_mtiles <= sm_count() && pl->NT >= 8) {
+    if (pl->S == 1 && 2 * pl->n_mtiles <= sm_count() && pl->NT >= 8) {
         int U = sm_count() / pl->n_mtiles;
         if (U > pl->NT / 2) U = pl->NT / 2;
         if (U > 16) U = 16;
@@ -692,6 +692,7 @@ static void make_plan(Plan* pl, int64_t n, int D, int K) {
         if (chunk < TM) chunk = (max_rows / TM > 0 ? max_rows / TM : 1) * TM;
         const int64_t need = ceil_div64(n, TM) * TM;
         if (chunk > need) chunk = need;
+        if (pl->U > 1 && chunk < need) { pl->U = 1; pl->nt_per_u = pl->NT; }     // unit splits need a single chunk
         pl->chunk_rows = chunk;
         o = align_up(o + (size_t)chunk * row_bytes, 1024);
     }
@@ -807,6 +808,8 @@ int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* 
             rc = launch(Pc);
             if (rc) return rc;
         }
+        if (pl.U > 1)       // few patch tiles: one chunk (make_plan), candidates of the unit splits merged here
+            return som_merge_candidates(P.cand_rd, P.cand_idx, pl.U, n, out_idx, out_rd, st);
         return SOM_OK;
     }
     rc = launch(P);
