@@ -214,3 +214,21 @@ def test_alternate_tensor_core_paths_in_a_subprocess(env):
                            capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, f"{env} {shp}: {r.stdout[-400:]} {r.stderr[-800:]}"
         assert "OK:" in r.stdout, r.stdout[-400:]
+
+
+@pytest.mark.parametrize("pd,fmaps", [((4, 4), 64), ((8, 8), 16)])
+def test_unit_split_keeps_the_first_of_duplicates_across_splits(pd, fmaps):
+    """Few patch tiles against >= 8 unit tiles: the tensor-core kernel spreads the unit tiles over CTAs and
+    merges candidates (resident-A mode at D = 64, streamed mode at D = 256).  The codebook is three copies of
+    the same 700 units, so every winner has exact duplicates in other splits: the lowest index must survive."""
+    x = synthetic_fmaps(fmaps, 5)
+    base = trained_like_codebook(700, pd, 17)
+    w = torch.cat([base, base, base], dim=0).contiguous()          # K = 2100 -> 9 unit tiles
+    oc = make_oracle_codebook(w, pd, (32, 32), 4, 700)
+    with torch.no_grad():
+        ref = oc.get_patches_bmu(x)
+    assert int(ref.max()) < 700
+    cb = _gpu_cb(w, pd, (32, 32), 4, 700, ops.SOM_BMU_TC3X)
+    idx = cb.get_patches_bmu(x.to(DEV)).cpu()
+    assert int(idx.max()) < 700, "a duplicate from a later unit split won"
+    assert_bmu_parity(idx, ref, flat_patches(x, pd), w)
