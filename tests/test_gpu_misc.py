@@ -295,3 +295,86 @@ def test_flat_and_backward_entry_points_match_their_general_forms():
     ws2 = torch.empty(nb2, dtype=torch.uint8, device=DEV)
     rc = lib.som_backward_nchw_f32(g_out.data_ptr(), *geom, ref.data_ptr(), k, rbar.data_ptr(), ws2.data_ptr(), nb2, st)
     assert rc == 0 and torch.equal(rbar, want)
+
+
+@pytest.mark.parametrize("k,n", [(12289, 70000), (32768, 1 << 20), (57344, 300001), (57345, 300001),
+                                 (262144, (1 << 21) + 5), (148 * 57344 + 1, 100000)])
+def test_histogram_range_partitioned_paths(k, n):
+    """Private shared-memory counters per unit range (1, 2 and 5 ranges), and the global-atomic path beyond
+    148 ranges; skewed hits, a base address that is only 8-byte aligned, out-of-range values next to range edges."""
+    g = torch.Generator().manual_seed(k % 1000)
+    idx = (torch.rand(n, generator=g).pow(3) * k).long().clamp_(0, k - 1)
+    idx[::5] = k - 1                                     # heavy hitter in the LAST range
+    idx[1::11] = 57343 % k                               # ... and one on a range edge
+    want = torch.bincount(idx, minlength=k)
+    dev = idx.to(DEV)
+    assert torch.equal(ops.histogram(dev, k).cpu(), want)
+    shifted = torch.empty(n + 1, dtype=torch.int64, device=DEV)
+    shifted[1:] = dev
+    assert torch.equal(ops.histogram(shifted[1:], k).cpu(), want)       # scalar (unaligned) loop
+    bad = idx.clone()
+    bad[:3] = torch.tensor([-1, k, -(1 << 40)])
+    assert int(ops.histogram(bad.to(DEV), k).sum()) == n - 3
+
+
+@pytest.mark.parametrize("shape,patch", [((5, 4, 32, 32), (2, 2)), ((3, 4, 32, 32), (4, 4)), ((3, 4, 32, 32), (8, 8)),
+                                         ((7, 4, 32, 32), (32, 32)), ((2, 3, 16, 24), (4, 2)), ((2, 3, 16, 24), (2, 4)),
+                                         ((2, 2, 12, 24), (3, 6)), ((3, 1, 8, 6), (2, 3)), ((2, 2, 8, 8), (1, 1)),
+                                         ((4101, 4, 32, 32), (4, 4))])
+def test_quantize_every_layout_matches_view_ops(shape, patch):
+    """Gather + fused unpatchify (output-ordered kernel for W % 4 == 0 with pW % 4 == 0 or pW == 2, patch-ordered
+    kernel otherwise) against table[idx] pushed through the reference's view-op unpatchify (models/layers.py:37-71)."""
+    n, c, h, w = shape
+    d = c * patch[0] * patch[1]
+    seq = (h // patch[0]) * (w // patch[1])
+    k = 37
+    g = torch.Generator().manual_seed(d)
+    table = torch.randn(k, d, generator=g)
+    idx = torch.randint(0, k, (n * seq,), generator=g)
+    want = somcb.unpatchify(table[idx].view(n, seq, d), image_dim=(h, w), patch_dim=patch)
+    geom = ops.geometry(shape, patch)
+    got = ops.quantize(idx.to(DEV), table.to(DEV), geom)
+    assert torch.equal(got.cpu(), want)
+    # guard band: an output view that is only 4-byte aligned takes the patch-ordered kernel and stays inside
+    buf = torch.full((n * c * h * w + 2,), 7.0, device=DEV)
+    ops.quantize(idx.to(DEV), table.to(DEV), geom, out=buf[1:-1].view(n, c, h, w))
+    assert torch.equal(buf[1:-1].view(n, c, h, w).cpu(), want)
+    assert float(buf[0]) == 7.0 and float(buf[-1]) == 7.0
+
+
+@pytest.mark.parametrize("k,d", [(1000, 256), (1000, 18), (513, 3), (70000, 16)])
+def test_gather_rows_matches_indexing(k, d):
+    g = torch.Generator().manual_seed(d)
+    w = torch.randn(k, d, generator=g)
+    keep = torch.nonzero(torch.rand(k, generator=g) < 0.4).flatten()
+    assert torch.equal(ops.gather_rows(w.to(DEV), keep.to(DEV)).cpu(), w[keep])
+
+
+@pytest.mark.parametrize("k,d", [(1, 16), (1000, 3), (4099, 8), (4099, 16), (4099, 17), (16385, 64), (77, 4096),
+                                 (300000, 16)])
+def test_codebook_norms_every_row_width(k, d):
+    """||c||^2 with 8-, 16- and 32-lane groups per unit against fp64."""
+    g = torch.Generator().manual_seed(k)
+    w = torch.randn(k, d, generator=g)
+    got = ops.prepare_codebook(w.to(DEV)).cpu().double()
+    want = w.double().pow(2).sum(1)
+    assert float(((got - want).abs() / want).max()) <= 2e-6
+
+
+def test_adam_kernel_vector_body_and_tail_agree():
+    """The 16-byte body and the scalar tail apply the same rule: a 4-byte-shifted view (scalar loop only) and the
+    aligned tensor (vector body + tail) give bit-identical results."""
+    g = torch.Generator().manual_seed(3)
+    n = 100003
+    w0, m0, gr = (torch.randn(n, generator=g).to(DEV) for _ in range(3))
+    v0 = torch.rand(n, generator=g).to(DEV)
+    res = []
+    for shift in (0, 1):
+        bufs = [torch.zeros(n + 1, device=DEV) for _ in range(4)]
+        views = [b[shift:shift + n] for b in bufs]
+        for dst, src in zip(views, (w0, m0, v0, gr)):
+            dst.copy_(src)
+        ops.adam_step(views[0], views[1], views[2], views[3], 1e-3, 5)
+        res.append([t.clone() for t in views[:3]])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
