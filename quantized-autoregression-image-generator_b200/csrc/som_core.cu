@@ -246,38 +246,40 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const int64_t* __r
                                                               int lr_seq, int hr_seq, int64_t lr_K, int64_t hr_K,
                                                               int base_model, int64_t* __restrict__ hr_input,
                                                               int64_t* __restrict__ hr_target) {
-    // a CTA walks fmaps; thread t owns columns t, t + 256, ... of the concatenated [hr_input | hr_target] row, so
-    // the loop has no integer division (one 64-bit division per element made the flat version instruction-bound)
+    // A thread owns ONE column (blockIdx.y * 256 + tid) of the concatenated [hr_input | hr_target] row, so where its
+    // value comes from (lr / hr index + shift, or a constant <start>/<end> token) is decided once; the CTA then walks
+    // fmaps four at a time with the four loads in flight.  No integer division in the loop (one 64-bit division per
+    // element kept the flat one-element-per-thread version at 60 % of the HBM copy rate).
     const int in_w = base_model ? lr_seq + hr_seq : 1 + hr_seq;
     const int row_w = in_w + hr_seq + 1;
-    constexpr int U = 4;
-    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
-        const int64_t* lrow = lr_idx + i * lr_seq;
-        const int64_t* hrow = hr_idx + i * hr_seq;
-        int64_t* irow = hr_input + i * in_w;
-        int64_t* trow = hr_target + i * (int64_t)(hr_seq + 1);
-        for (int c0 = threadIdx.x; c0 < row_w; c0 += U * 256) {
-            int64_t val[U];
-            int64_t* dst[U];
+    const int c = blockIdx.y * 256 + threadIdx.x;
+    if (c >= row_w) return;
+    const int64_t* src = nullptr;          // nullptr: constant column
+    int64_t sstride = 0, add = 0, cval = hr_K;
+    int64_t* dst;
+    int64_t dstride;
+    if (c < in_w) {
+        dst = hr_input + c; dstride = in_w;
+        if (base_model) {
+            if (c < lr_seq) { src = lr_idx + c; sstride = lr_seq; }
+            else { src = hr_idx + (c - lr_seq); sstride = hr_seq; add = lr_K; }
+        } else if (c > 0) { src = hr_idx + (c - 1); sstride = hr_seq; }
+    } else {
+        const int kk = c - in_w;
+        dst = hr_target + kk; dstride = hr_seq + 1;
+        if (kk < hr_seq) { src = hr_idx + kk; sstride = hr_seq; }
+    }
+    constexpr int R = 4;
+    for (int64_t i0 = (int64_t)blockIdx.x * R; i0 < n; i0 += (int64_t)gridDim.x * R) {
+        int64_t val[R];
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const int c = c0 + k * 256;
-                dst[k] = nullptr;
-                if (c >= row_w) continue;
-                if (c < in_w) {
-                    if (base_model) val[k] = (c < lr_seq) ? __ldg(lrow + c) : __ldg(hrow + (c - lr_seq)) + lr_K;
-                    else val[k] = (c == 0) ? hr_K : __ldg(hrow + (c - 1));
-                    dst[k] = irow + c;
-                } else {
-                    const int kk = c - in_w;
-                    val[k] = (kk < hr_seq) ? __ldg(hrow + kk) : hr_K;
-                    dst[k] = trow + kk;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < U; ++k)
-                if (dst[k] != nullptr) __stcs(dst[k], val[k]);
+        for (int k = 0; k < R; ++k) {
+            val[k] = cval;
+            if (src != nullptr && i0 + k < n) val[k] = __ldg(src + (i0 + k) * sstride) + add;
         }
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+            if (i0 + k < n) __stcs(dst + (i0 + k) * dstride, val[k]);
     }
 }
 
@@ -640,7 +642,11 @@ int som_assemble_tokens_i64(const int64_t* lr_idx, const int64_t* hr_idx, int64_
     SOM_REQUIRE(n >= 0 && hr_seq > 0 && lr_seq >= 0, SOM_E_BADARG, "assemble_tokens: n=%lld lr_seq=%d hr_seq=%d",
                 (long long)n, lr_seq, hr_seq);
     if (n == 0) return SOM_OK;
-    int blocks = (int)(n < (int64_t)sm_count() * 8 ? n : (int64_t)sm_count() * 8);
+    const int row_w = (base_model ? lr_seq + hr_seq : 1 + hr_seq) + hr_seq + 1;
+    const int gy = (row_w + 255) / 256;
+    int64_t gx = ceil_div64(n, 4), cap = (int64_t)sm_count() * 16 / gy;
+    if (cap < 1) cap = 1;
+    dim3 blocks((unsigned)(gx < cap ? gx : cap), (unsigned)gy);
     assemble_tokens_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(lr_idx, hr_idx, n, lr_seq, hr_seq, lr_K, hr_K,
                                                                      base_model, hr_input, hr_target);
     return check_launch("assemble_tokens_kernel");
