@@ -17,6 +17,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
          "-Xptxas", "-v", "-DSOM_BUILDING_LIB"]
+FLAGS += os.environ.get("SOMCB_EXTRA_NVCC_FLAGS", "").split()        # e.g. -DSOM_TC_EXPERIMENTS (tools/ only)
 
 
 def _deps_mtime():
