@@ -102,6 +102,15 @@ SOM_API int som_histogram_i64(const int64_t* idx, int64_t n, int K, int64_t* cou
 SOM_API int som_filter_f32(const float* in, float* out, int K, int D, double neighbourhood_range,
                    float scale, void* stream);
 
+/* The same filter with a caller-owned workspace: for K >= 256 units and rows of >= 48 features it runs as a
+ * banded-Toeplitz GEMM on the tensor cores (tcgen05 kind::tf32, fp32-faithful 3xTF32; the workspace holds the
+ * transposed hi | lo split of `in`), otherwise -- or with ws == NULL -- it is som_filter_f32.  Replaces the dense
+ * S @ W (models/Codebook.py:128-130) and its autograd transpose like som_filter_f32.
+ * som_filter_workspace_bytes returns 0 when the shape takes the FFMA kernel.                               */
+SOM_API size_t som_filter_workspace_bytes(int K, int D, double neighbourhood_range);
+SOM_API int som_filter_ws_f32(const float* in, float* out, int K, int D, double neighbourhood_range,
+                      float scale, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K2: per-unit accumulation (segmented by BMU, deterministic, no float atomics) ------
  *   Wt != NULL:  Rbar[a] = sum_{p: bmu[p]==a} (Wt[a] - x_p),  sse = sum_p ||Wt[bmu_p]-x_p||^2
  *   Wt == NULL:  Rbar[a] = sum_{p: bmu[p]==a} x_p             (autograd backward of the gather)

@@ -224,9 +224,44 @@ static int host_band_half_width(float two_var, int K) {
     return (int)t;
 }
 
+int filter_band_half_width(float two_var, int K) { return host_band_half_width(two_var, K); }
+
+// som_filter_tc.cu
+bool filter_tc_applicable(int K, int D, int h);
+size_t filter_tc_workspace_bytes(int K, int D, int h);
+int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, int h, float scale, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
+
+// models/Codebook.py:118 -- Python double arithmetic, then one rounding to fp32 at the divide
+static inline float two_var_of(double neighbourhood_range) {
+    const double variance = -(neighbourhood_range / (2.0 * log(0.1)));
+    return (float)(2.0 * variance);
+}
+
 }  // namespace som
 
 using namespace som;
+
+extern "C" size_t som_filter_workspace_bytes(int K, int D, double neighbourhood_range) {
+    if (K <= 0 || D <= 0 || !(neighbourhood_range > 0.0)) return 0;
+    const float two_var = two_var_of(neighbourhood_range);
+    const int h = host_band_half_width(two_var, K);
+    return filter_tc_applicable(K, D, h) ? filter_tc_workspace_bytes(K, D, h) : 0;
+}
+
+extern "C" int som_filter_ws_f32(const float* in, float* out, int K, int D, double neighbourhood_range, float scale,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    SOM_REQUIRE(in && out, SOM_E_BADARG, "filter: null pointer");
+    SOM_REQUIRE(in != out, SOM_E_BADARG, "filter: in-place operation is not supported");
+    SOM_REQUIRE(K > 0 && D > 0, SOM_E_BADARG, "filter: K=%d D=%d", K, D);
+    SOM_REQUIRE(neighbourhood_range > 0.0, SOM_E_BADARG, "filter: neighbourhood_range=%g", neighbourhood_range);
+    const float two_var = two_var_of(neighbourhood_range);
+    const int h = host_band_half_width(two_var, K);
+    // static rule on the shape: tensor cores for K >= 256 units and rows of >= 48 features (som_filter_tc.cu)
+    if (filter_tc_applicable(K, D, h) && ws != nullptr)
+        return launch_filter_tc(in, out, K, D, two_var, h, scale, ws, ws_bytes, (cudaStream_t)stream);
+    return som_filter_f32(in, out, K, D, neighbourhood_range, scale, stream);
+}
 
 extern "C" int som_filter_f32(const float* in, float* out, int K, int D,
                               double neighbourhood_range, float scale, void* stream) {

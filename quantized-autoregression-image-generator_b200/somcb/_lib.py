@@ -31,6 +31,9 @@ SIGNATURES = {
     "som_merge_candidates": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "som_histogram_i64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "som_filter_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p]),
+    "som_filter_workspace_bytes": (c_size_t, [c_int, c_int, c_double]),
+    "som_filter_ws_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_size_t,
+                                  c_void_p]),
     "som_accumulate_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "som_accumulate_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

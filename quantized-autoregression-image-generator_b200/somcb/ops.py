@@ -141,8 +141,9 @@ def histogram(idx, num_units, counts=None):
     return counts
 
 
-def neighbourhood_filter(inp, neighbourhood_range, scale=1.0, out=None):
-    """K3.  out = scale * T @ inp along the unit axis."""
+def neighbourhood_filter(inp, neighbourhood_range, scale=1.0, out=None, tensor_cores=True):
+    """K3.  out = scale * T @ inp along the unit axis.  ``tensor_cores=False`` forces the FFMA kernel
+    (the library picks by shape otherwise: tcgen05 for K >= 256 and D >= 48)."""
     lib = _lib.load()
     inp = _req(inp, torch.float32, "inp")
     k, d = inp.shape
@@ -150,9 +151,15 @@ def neighbourhood_filter(inp, neighbourhood_range, scale=1.0, out=None):
         out = torch.empty_like(inp)
     out = _req(out, torch.float32, "out")
     with torch.cuda.device(inp.device):
-        check("som_filter_f32",
-              lib.som_filter_f32(_ptr(inp), _ptr(out), k, d, float(neighbourhood_range), float(scale),
-                                 _stream(inp)))
+        if not tensor_cores:
+            check("som_filter_f32",
+                  lib.som_filter_f32(_ptr(inp), _ptr(out), k, d, float(neighbourhood_range), float(scale),
+                                     _stream(inp)))
+            return out
+        ws, ws_bytes = _workspace(lib.som_filter_workspace_bytes(k, d, float(neighbourhood_range)), inp.device)
+        check("som_filter_ws_f32",
+              lib.som_filter_ws_f32(_ptr(inp), _ptr(out), k, d, float(neighbourhood_range), float(scale),
+                                    _ptr(ws), ws_bytes, _stream(inp)))
     return out
 
 

@@ -42,6 +42,39 @@ def test_filter_matches_dense_toeplitz(k, d, rng):
     assert_close_norm(got2, want * 0.125, 2e-6, "scaled T@W")
 
 
+@pytest.mark.parametrize("k,d,rng", [(1024, 64, 512), (512, 4096, 256), (300, 50, 40), (4100, 50, 40), (1000, 530, 3),
+                                     (300, 4096, 0.5), (4096, 64, 2048), (2100, 200, 4000.0), (640, 64, 1.0)])
+def test_filter_tensor_core_and_ffma_kernels_agree(k, d, rng):
+    """K >= 256, D >= 48 and at least 32 tiles take the tcgen05 banded-Toeplitz GEMM (fp32-faithful 3xTF32; here
+    cases 2, 4, 5, 6, 7 and 8): both kernels must agree
+    with the dense fp64 product -- partial unit tiles, feature counts that are not multiples of 4 / 32 / the tile,
+    bands from one unit to wider than the codebook, a non-trivial scale, guard bands around the output."""
+    g = torch.Generator().manual_seed(k * 7 + d)
+    w = torch.randn(k, d, generator=g)
+    want = 0.37 * (_dense_t(k, rng) @ w.double())
+    wd = w.to(DEV)
+    for tc in (True, False):
+        buf = torch.full((k * d + 8,), 7.0, device=DEV)
+        out = (buf[4:-4] if k % 2 else buf[5:-3]).view(k, d)          # 16-byte aligned / 4-byte aligned output
+        ops.neighbourhood_filter(wd, rng, scale=0.37, out=out, tensor_cores=tc)
+        assert_close_norm(out, want, 2e-6, f"T@W tensor_cores={tc}")
+        assert float((out.double().cpu() - want).abs().max()) <= 2e-6 * float(want.abs().max())
+        assert bool((buf[:4] == 7.0).all()) and bool((buf[-3:] == 7.0).all())
+    a = ops.neighbourhood_filter(wd, rng)
+    b = ops.neighbourhood_filter(wd, rng)
+    assert torch.equal(a, b)                                     # deterministic
+
+
+def test_filter_c4_shape_tensor_core_vs_ffma():
+    """BASELINE C4 codebook (K = 16384, D = 64, range 8192: band 1217): too large for the dense fp64 check, so the
+    two kernels are compared with each other."""
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(16384, 64, generator=g).to(DEV)
+    a = ops.neighbourhood_filter(w, 8192)
+    b = ops.neighbourhood_filter(w, 8192, tensor_cores=False)
+    assert_close_norm(a, b.double().cpu(), 2e-6, "tensor-core vs FFMA filter")
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_accumulate_matches_index_add(name):
     rec = load_case(name)
