@@ -763,15 +763,15 @@ int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* 
         {bmu_tc_l_kernel<true, false, 1>, bmu_tc_l_kernel<false, true, 1>, bmu_tc_l_kernel<false, false, 1>},
         {bmu_tc_l_kernel<true, false, 2>, bmu_tc_l_kernel<false, true, 2>, bmu_tc_l_kernel<false, false, 2>}};
     static const char* names[3] = {"bmu_tc_l_kernel<splitk>", "bmu_tc_l_kernel<resident>", "bmu_tc_l_kernel<streamed>"};
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceFlag attr_done;
+    if (attr_done.pending()) {
         for (int c = 0; c < 2; ++c)
             for (int m = 0; m < 3; ++m) {
                 cudaError_t e = cudaFuncSetAttribute(kernels[c][m], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int)SMEM_BYTES);
                 if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
             }
-        attr_done = true;
+        attr_done.set();
     }
     auto launch = [&](const Params& Pl) -> int {
         const int n_jobs = ((Pl.n_mtiles + pl.cg - 1) / pl.cg) * pl.S * pl.U;

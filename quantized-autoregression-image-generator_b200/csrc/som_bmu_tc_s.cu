@@ -497,11 +497,11 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
     // timing-elimination switches (skip refine / loads / conversion): results are wrong, experiment builds only
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SOM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
 #endif
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceFlag attr_done;
+    if (attr_done.pending()) {
         cudaError_t e = cudaFuncSetAttribute(bmu_tc_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_done = true;
+        attr_done.set();
     }
     // small batches: fewer resident tiles per CTA so that every SM gets a super-tile (a unit tile then feeds
     // fewer MMAs, but the sweep over the unit tiles is what bounds a small batch)

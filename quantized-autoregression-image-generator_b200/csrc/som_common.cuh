@@ -20,6 +20,15 @@ unsigned long long launch_count();
     do { if (!(cond)) return ::som::fail((code), __VA_ARGS__); } while (0)
 
 int sm_count();                                // cached per process (device 0..n: current device)
+int current_device();                          // cudaGetDevice, -1 on error
+
+// cudaFuncSetAttribute is per device: "done once" flags are kept per device ordinal (a process may drive several
+// GPUs).  Setting an attribute twice is harmless, so the flag needs no lock.
+struct PerDeviceFlag {
+    bool done[64] = {};
+    bool pending() const { const int d = current_device(); return d < 0 || d >= 64 || !done[d]; }
+    void set() { const int d = current_device(); if (d >= 0 && d < 64) done[d] = true; }
+};
 
 // ---- patch geometry ------------------------------------------------------------------------
 // offset(p, d) = patch_base(p) + feat_off(d): patchify (models/layers.py:8-34) is separable, so

@@ -38,6 +38,11 @@ int check_launch(const char* what) {
 
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+int current_device() {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int sm_count() {
     static int cached[64];
     static std::once_flag once;

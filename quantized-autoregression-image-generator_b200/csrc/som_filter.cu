@@ -276,26 +276,26 @@ extern "C" int som_filter_f32(const float* in, float* out, int K, int D,
     int h = host_band_half_width(two_var, K);
     size_t smem = (size_t)(2 * (h + FILT_PAD) + 1) * sizeof(float);
     SOM_REQUIRE(smem <= 200 * 1024, SOM_E_SHAPE, "filter: band half-width %d too large", h);
-    static bool attr_set = false;   // idempotent; worst case it is set twice
-    if (smem > 48 * 1024 && !attr_set) {
+    static PerDeviceFlag attr_set;   // idempotent; worst case it is set twice
+    if (smem > 48 * 1024 && attr_set.pending()) {
         cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              200 * 1024);
         if (e != cudaSuccess) { set_error("filter: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
+        attr_set.set();
     }
     if ((D & 3) == 0 && D >= 48 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
         const int td = D >= 128 ? 128 : 64;
         const size_t tab_n = (size_t)(2 * (h + FT_PAD) + 1);
         const size_t smem_t = ((tab_n + 3) & ~(size_t)3) * sizeof(float) + 2 * (size_t)FT_JC * td * sizeof(float);
         SOM_REQUIRE(smem_t <= 200 * 1024, SOM_E_SHAPE, "filter: band half-width %d too large", h);
-        static bool attr_t = false;
-        if (!attr_t) {
+        static PerDeviceFlag attr_t;
+        if (attr_t.pending()) {
             cudaError_t e = cudaFuncSetAttribute(filter_tile_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  200 * 1024);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(filter_tile_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) { set_error("filter: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
-            attr_t = true;
+            attr_t.set();
         }
         dim3 gt((unsigned)ceil_div64(K, 32), (unsigned)ceil_div64(D, td));      // 32 units per CTA in both shapes
         if (td == 128) filter_tile_kernel<128, 2><<<gt, FT_THREADS, smem_t, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);

@@ -331,13 +331,13 @@ int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, i
     Params P;
     P.K = K; P.D = D; P.h = h; P.nkb = pl.nkb; P.two_var = two_var; P.scale = scale; P.out = out;
     const size_t smem = smem_bytes(pl.tnf, h);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceFlag attr_done;
+    if (attr_done.pending()) {
         cudaError_t e = cudaFuncSetAttribute(filter_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(filter_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("filter(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_done = true;
+        attr_done.set();
     }
     dim3 grid((unsigned)ceil_div64(K, TMU), (unsigned)ceil_div64(D, pl.tnf));
     if (pl.tnf == 128) filter_tc_kernel<128><<<grid, NUM_THREADS, smem, st>>>(map_bhi, map_blo, P);
