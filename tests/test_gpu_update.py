@@ -129,6 +129,32 @@ def test_accumulate_skewed_segments(pattern):
     assert abs(float(sse) - float((r ** 2).sum())) <= 5e-6 * float((r ** 2).sum())
 
 
+@pytest.mark.parametrize("fmaps,k", [(33, 300), (79, 300), (128, 16384), (129, 300), (20, 70000), (1, 70000)])
+def test_accumulate_small_and_medium_batches(fmaps, k):
+    """64 to 8256 patches, codebooks of 300 to 70000 units (K = 70000 keeps tiny batches off the scan path, so the
+    sorted path also sees them): fp64 index_add, counts, empty units exactly zero, SSE, bit-identical repeat."""
+    pd = (4, 4)
+    x = synthetic_fmaps(fmaps, 5 + fmaps)
+    flat = flat_patches(x, pd).double()
+    n = flat.shape[0]
+    g = torch.Generator().manual_seed(n)
+    bmu = torch.randint(0, k, (n,), generator=g)
+    bmu[::3] = bmu[0]                                       # a heavy hitter
+    table = torch.randn(k, 64, generator=g)
+    xd, geom = x.to(DEV), ops.geometry(x.shape, pd)
+    rbar, counts, sse = ops.accumulate(xd, geom, bmu.to(DEV), table.to(DEV), k, want_counts=True, want_sse=True)
+    r = table.double()[bmu] - flat
+    want = torch.zeros(k, 64, dtype=torch.float64).index_add_(0, bmu, r)
+    assert_close_norm(rbar, want, 5e-6, "Rbar")
+    hits = torch.bincount(bmu, minlength=k)
+    assert torch.equal(counts.cpu(), hits)
+    if bool((hits == 0).any()):
+        assert float(rbar.cpu()[hits == 0].abs().max()) == 0.0
+    assert abs(float(sse) - float((r ** 2).sum())) <= 5e-6 * float((r ** 2).sum())
+    rbar2, _, sse2 = ops.accumulate(xd, geom, bmu.to(DEV), table.to(DEV), k, want_sse=True)
+    assert torch.equal(rbar, rbar2) and torch.equal(sse, sse2)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_quantize_paths_match_reference(name):
     rec = load_case(name)
