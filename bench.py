@@ -343,6 +343,9 @@ def main():
 
     # ---- end to end from pinned host memory through the public host API ----------------------
     e2e_steps = args.e2e_steps or min(args.steps, 10)
+    # one process per GPU: stage out of the GPU's own NUMA node (no-op when the topology is not exposed)
+    cpus_before = os.sched_getaffinity(0)
+    numa_node = somcb.bind_host_to_gpu_node(dev)
     host = torch.empty(C2["n_fmaps"], C2["C"], C2["H"], C2["W"], pin_memory=True)
     host.copy_(x)
     out_host = torch.empty(C2["n_fmaps"], 256, dtype=torch.int64, pin_memory=True)
@@ -359,13 +362,15 @@ def main():
     f1.record()
     torch.cuda.synchronize()
     assert torch.equal(out_host, idx.cpu()), "e2e indices differ from the resident-input run"
+    os.sched_setaffinity(0, cpus_before)            # the CPU baseline below uses every host core again
     e2e_t = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t) / e2e_steps
     e2e = {"value": world * n_p / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
            "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 8,
-           "api": "somcb.HostTokenizer.tokenize(pinned fmaps) -> pinned int64 indices"}
+           "api": "somcb.HostTokenizer.tokenize(pinned fmaps) -> pinned int64 indices",
+           "host_numa_node": numa_node}
 
     # ---- roofline of the dominant kernel (BMU) --------------------------------------------------
     flops = 2.0 * k * d_dim * n_p

@@ -12,10 +12,10 @@ from .layers import patchify, unpatchify  # noqa: E402,F401
 from .trainer import SomTrainer, prune_codebook, bmu_histogram  # noqa: E402,F401
 from .distributed import (  # noqa: E402,F401
     DataParallelSom, sharded_bmu, shard_bounds, split_batch)
-from .host_pipeline import HostTokenizer  # noqa: E402,F401
+from .host_pipeline import HostTokenizer, bind_host_to_gpu_node  # noqa: E402,F401
 from .tokenizer import tokenize_pair  # noqa: E402,F401
 from . import fmap_shards  # noqa: E402,F401
 from .fmap_shards import ShardReader, convert_reference_dataset  # noqa: E402,F401
 
 __all__ = ["Codebook", "patchify", "unpatchify", "SomTrainer", "prune_codebook", "bmu_histogram",
-           "DataParallelSom", "sharded_bmu", "shard_bounds", "split_batch", "HostTokenizer", "tokenize_pair", "ShardReader", "convert_reference_dataset", "ops"]
+           "DataParallelSom", "sharded_bmu", "shard_bounds", "split_batch", "HostTokenizer", "bind_host_to_gpu_node", "tokenize_pair", "ShardReader", "convert_reference_dataset", "ops"]
