@@ -179,3 +179,12 @@ def test_fmap_shards_round_trip_from_reference_layout(tmp_path):
     bad.write_bytes(b"x" * 100)
     with pytest.raises(ValueError):
         fs.read_header(str(bad))
+
+
+def test_numa_binding_is_a_noop_without_topology():
+    """No CUDA device / no sysfs topology: bind_host_to_gpu_node returns None and leaves the affinity alone."""
+    import os
+    before = os.sched_getaffinity(0)
+    assert somcb.bind_host_to_gpu_node() is None
+    assert somcb.bind_host_to_gpu_node("cuda:0") is None
+    assert os.sched_getaffinity(0) == before
