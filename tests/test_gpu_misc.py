@@ -378,3 +378,30 @@ def test_adam_kernel_vector_body_and_tail_agree():
         res.append([t.clone() for t in views[:3]])
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+def test_filter_ws_entry_point_contract():
+    """som_filter_ws_f32: workspace size query is 0 for shapes that take the FFMA kernel; a NULL workspace falls back
+    to som_filter_f32 (bit-identical); a short workspace is SOM_E_WORKSPACE; in-place and NULL arguments are rejected."""
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(4096, 64, generator=g).to(DEV)
+    need = lib.som_filter_workspace_bytes(4096, 64, 2048.0)
+    assert need > 0
+    assert lib.som_filter_workspace_bytes(1024, 64, 512.0) == 0          # 8 tiles: FFMA kernel
+    assert lib.som_filter_workspace_bytes(4096, 16, 2048.0) == 0         # short rows: FFMA kernel
+    assert lib.som_filter_workspace_bytes(0, 64, 2048.0) == 0
+    a, b = torch.empty_like(w), torch.empty_like(w)
+    rc = lib.som_filter_ws_f32(w.data_ptr(), a.data_ptr(), 4096, 64, 2048.0, 1.0, None, 0, st)
+    assert rc == 0
+    assert lib.som_filter_f32(w.data_ptr(), b.data_ptr(), 4096, 64, 2048.0, 1.0, st) == 0
+    assert torch.equal(a, b)
+    ws = torch.empty(need, dtype=torch.uint8, device=DEV)
+    rc = lib.som_filter_ws_f32(w.data_ptr(), a.data_ptr(), 4096, 64, 2048.0, 1.0, ws.data_ptr(), need - 1, st)
+    assert rc == -3 and b"workspace" in lib.som_last_error()
+    assert lib.som_filter_ws_f32(w.data_ptr(), a.data_ptr(), 4096, 64, 2048.0, 1.0, ws.data_ptr(), need, st) == 0
+    assert float((a - b).norm() / b.norm()) <= 2e-6                     # tensor-core vs FFMA result
+    assert lib.som_filter_ws_f32(w.data_ptr(), w.data_ptr(), 4096, 64, 2048.0, 1.0, ws.data_ptr(), need, st) == -1
+    assert lib.som_filter_ws_f32(None, a.data_ptr(), 4096, 64, 2048.0, 1.0, ws.data_ptr(), need, st) == -1
+    assert lib.som_filter_ws_f32(w.data_ptr(), a.data_ptr(), 4096, 64, -1.0, 1.0, ws.data_ptr(), need, st) == -1
