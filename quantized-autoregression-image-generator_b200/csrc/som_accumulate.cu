@@ -38,10 +38,16 @@ struct AccumPlan {
         off_cub, cub_bytes, total;
 };
 
-static int pick_chunk(int64_t n) {
+// Sorted positions per level-1 chunk: enough (chunk, feature slice) warps to fill the machine, but no shorter chunks
+// than that needs -- every chunk pays the key fetch, up to two partial segments and the W~ row of its first unit.
+// Long rows bring their own parallelism (one warp per 128-feature slice): C3 (4096 patches, D = 4096) gets S = 32
+// instead of 8 (accumulate 70.7 -> 58.6 us).  Large batches are flat in S (C4 shape: 0.39 / 0.36 / 0.35 / 0.34 / 0.36 /
+// 0.43 ms at S = 8 / 16 / 32 / 64 / 128 / 256), so 64 stays the cap.
+static int pick_chunk(int64_t n, int D) {
     const int64_t target = 148 * 16;
+    const int64_t slices = D >= 128 ? D / 128 : 1;
     int S = 64;
-    while (S > 8 && n / S < target) S >>= 1;
+    while (S > 8 && (n / S) * slices < target) S >>= 1;
     return S;
 }
 
@@ -49,7 +55,7 @@ static int make_plan(AccumPlan* pl, int64_t n, int D, int K, bool query_cub) {
     SOM_REQUIRE(n >= 0 && n < (int64_t)INT32_MAX && D > 0 && K > 0, SOM_E_BADARG,
                 "accumulate: n=%lld D=%d K=%d out of range", (long long)n, D, K);
     pl->n = n; pl->D = D; pl->K = K;
-    pl->S = pick_chunk(n);
+    pl->S = pick_chunk(n, D);
     pl->n_chunks = n > 0 ? ceil_div64(n, pl->S) : 0;
     pl->n_slices_max = (D + 31) / 32;
     int bits = 1;
