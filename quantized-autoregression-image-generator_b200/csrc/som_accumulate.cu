@@ -133,7 +133,7 @@ __device__ __forceinline__ void store_vec(float* p, const float (&r)[VEC]) {
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(ACC_WARPS * 32)
+__global__ void __launch_bounds__(ACC_WARPS * 32, VEC == 4 ? 3 : 4)
 seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ skey,
                   const int* __restrict__ sid, const int* __restrict__ offsets,
                   const float* __restrict__ Wt, float* __restrict__ Rbar,
