@@ -119,6 +119,32 @@ __global__ void __launch_bounds__(256) norm2_kernel(const float* __restrict__ W,
     }
 }
 
+// Long rows (D >= 2048: the whole-fmap codebook, a few hundred units of 16 KB): one CTA per unit, because one warp
+// per four units leaves most SMs without work (C3: 128 warps, 16 us for 8 MB).  Thread t adds d = t, t + 256, ... in
+// order (four loads in flight), then a warp butterfly and the eight warp sums in warp order: fixed order, and the
+// rule depends on D only, so a unit's norm does not depend on how many units the launch (or the shard) holds.
+__global__ void __launch_bounds__(256) norm2_long_kernel(const float* __restrict__ W, int D, float* __restrict__ out) {
+    __shared__ float part[8];
+    const float* row = W + (int64_t)blockIdx.x * D;
+    float s = 0.f;
+    for (int d0 = threadIdx.x; d0 < D; d0 += 4 * 256) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (d0 + 256 * j < D) ? __ldg(row + d0 + 256 * j) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s = fmaf(v[j], v[j], s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = part[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += part[w];
+        out[blockIdx.x] = t;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1b: candidate merge
 // ---------------------------------------------------------------------------------------------
@@ -541,6 +567,10 @@ int som_prepare_codebook_f32(const float* W, int K, int D, float* c_norm2, void*
     SOM_REQUIRE(W && c_norm2, SOM_E_BADARG, "prepare_codebook: null pointer");
     SOM_REQUIRE(K > 0 && D > 0, SOM_E_BADARG, "prepare_codebook: K=%d D=%d", K, D);
     cudaStream_t st = (cudaStream_t)stream;
+    if (D >= 2048) {
+        norm2_long_kernel<<<(unsigned)K, 256, 0, st>>>(W, D, c_norm2);
+        return check_launch("norm2_long_kernel");
+    }
     if (D > 16) {            // 4 units x 4 row segments in flight per lane
         int blocks = grid_for(ceil_div64(K, 4) * 32, 256, 8);
         norm2_kernel<32, 4, 4><<<blocks, 256, 0, st>>>(W, K, D, c_norm2);
