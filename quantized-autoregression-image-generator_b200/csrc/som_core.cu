@@ -606,6 +606,8 @@ int som_histogram_i64(const int64_t* idx, int64_t n, int K, int64_t* counts, voi
     }
     const int sms = sm_count();
     const int P = (int)ceil_div64(K, HIST_RANGE_MAX);
+    // also for few indices per unit (C5 shard, 2^20 indices against 32768 units: 12.7-14.3 us, the same as direct
+    // global atomics on uniform hits) -- skewed hits would serialise on one L2 address there
     if (P <= sms) {
         static std::once_flag once[64];
         int dev = 0;

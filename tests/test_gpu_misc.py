@@ -297,11 +297,14 @@ def test_flat_and_backward_entry_points_match_their_general_forms():
     assert rc == 0 and torch.equal(rbar, want)
 
 
-@pytest.mark.parametrize("k,n", [(12289, 70000), (32768, 1 << 20), (57344, 300001), (57345, 300001),
-                                 (262144, (1 << 21) + 5), (148 * 57344 + 1, 100000)])
+@pytest.mark.parametrize("k,n", [(12289, 800001), (32768, 1 << 21), (57344, 3670017), (57345, 3670081),
+                                 (262144, (1 << 24) + 5),                       # range kernel: 1, 1, 1, 2, 5 ranges
+                                 (12289, 70000), (32768, 1 << 20), (262144, (1 << 21) + 5),   # few indices per unit
+                                 (148 * 57344 + 1, 100000)])                    # more ranges than SMs
 def test_histogram_range_partitioned_paths(k, n):
-    """Private shared-memory counters per unit range (1, 2 and 5 ranges), and the global-atomic path beyond
-    148 ranges; skewed hits, a base address that is only 8-byte aligned, out-of-range values next to range edges."""
+    """Private shared-memory counters per unit range (1, 2 and 5 ranges; many and few indices per unit), direct global
+    atomics beyond 148 ranges; skewed hits, a base address that is only 8-byte aligned, out-of-range
+    values next to range edges."""
     g = torch.Generator().manual_seed(k % 1000)
     idx = (torch.rand(n, generator=g).pow(3) * k).long().clamp_(0, k - 1)
     idx[::5] = k - 1                                     # heavy hitter in the LAST range
