@@ -545,10 +545,23 @@ __global__ void __launch_bounds__(256) splitk_argmin_kernel(const float* __restr
     if (p >= rows) return;
     float best = INFINITY;
     int bidx = 0x7fffffff;
-    for (int j = lane; j < K; j += 32) {
-        float v = 0.f;
-        for (int s = 0; s < S; ++s) v += partial[((int64_t)s * n_pad + p) * K_pad + j];
-        if (v < best) { best = v; bidx = j; }
+    // 16-byte loads: lane l owns units 128 i + 4 l .. + 3 (K_pad is a multiple of 256, rows are 1 KB aligned), all S
+    // partial rows of an iteration in flight; per lane the units are still visited in ascending order
+    const float4* prow = reinterpret_cast<const float4*>(partial + p * K_pad);
+    const int64_t sstride = n_pad * (int64_t)K_pad / 4;
+    for (int j0 = 4 * lane; j0 < K; j0 += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 t[MAX_SPLIT];
+#pragma unroll
+        for (int s = 0; s < MAX_SPLIT; ++s)
+            if (s < S) t[s] = __ldcs(prow + (int64_t)s * sstride + (j0 >> 2));
+#pragma unroll
+        for (int s = 0; s < MAX_SPLIT; ++s)
+            if (s < S) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }
+        if (acc.x < best) { best = acc.x; bidx = j0; }
+        if (j0 + 1 < K && acc.y < best) { best = acc.y; bidx = j0 + 1; }
+        if (j0 + 2 < K && acc.z < best) { best = acc.z; bidx = j0 + 2; }
+        if (j0 + 3 < K && acc.w < best) { best = acc.w; bidx = j0 + 3; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
