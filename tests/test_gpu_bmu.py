@@ -232,3 +232,26 @@ def test_unit_split_keeps_the_first_of_duplicates_across_splits(pd, fmaps):
     idx = cb.get_patches_bmu(x.to(DEV)).cpu()
     assert int(idx.max()) < 700, "a duplicate from a later unit split won"
     assert_bmu_parity(idx, ref, flat_patches(x, pd), w)
+
+
+@pytest.mark.parametrize("fmaps,p,k,bound", [(64, 32, 512, 5e-6), (32, 8, 2048, 3e-6), (16, 4, 4096, 1e-6),
+                                              (64, 2, 4096, 1e-6)])
+def test_reduced_distance_accuracy_of_both_variants(fmaps, p, k, bound):
+    """The returned reduced distance rd = ||c||^2 - 2 x.c against fp64, relative to ||c||^2 + 2 sum|x c|.  The
+    tensor-core variant carries the truncation bias of the fp32 TMEM accumulator (measured -2e-6 at D = 4096,
+    -9e-7 at D = 256, -1e-7 at D = 64: DESIGN 5); the bound guards the accumulation scheme against regressions."""
+    pd = (p, p)
+    d = 4 * p * p
+    x = synthetic_fmaps(fmaps, 17)
+    w = trained_like_codebook(k, pd, 3)
+    flat = flat_patches(x, pd).double()
+    geom = ops.geometry(x.shape, pd)
+    xd, wd = x.to(DEV), w.to(DEV)
+    cn = ops.prepare_codebook(wd)
+    for variant in _variants(flat.shape[0], d, k):
+        idx, rd = ops.bmu(xd, geom, wd, cn, want_rd=True, variant=variant)
+        wi = w.double()[idx.cpu()]
+        true = (wi * wi).sum(1) - 2 * (flat * wi).sum(1)
+        scale = (wi * wi).sum(1) + 2 * (flat * wi).abs().sum(1)
+        err = float(((rd.double().cpu() - true).abs() / scale).max())
+        assert err <= bound, f"variant {variant}: rd error {err:.2e} > {bound}"
