@@ -570,6 +570,9 @@ __global__ void __launch_bounds__(256) splitk_argmin_kernel(const float* __restr
         if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
     }
     if (lane == 0) {
+        // a non-finite patch row makes every sum NaN and no '<' fires: unit 0 of the shard, as torch.argmin over an
+        // all-NaN distance row does (models/Codebook.py:91-94) and as the other modes' "best = inf, index 0" start does
+        if (bidx == 0x7fffffff) bidx = 0;
         out_idx[p] = (int64_t)bidx + unit_offset;
         if (out_rd) out_rd[p] = best;
     }

@@ -255,3 +255,49 @@ def test_reduced_distance_accuracy_of_both_variants(fmaps, p, k, bound):
         scale = (wi * wi).sum(1) + 2 * (flat * wi).abs().sum(1)
         err = float(((rd.double().cpu() - true).abs() / scale).max())
         assert err <= bound, f"variant {variant}: rd error {err:.2e} > {bound}"
+
+
+@pytest.mark.parametrize("fmaps,p,k", [(64, 2, 4096), (16, 4, 4096), (64, 4, 2100), (32, 8, 2048), (16, 8, 20000),
+                                       (64, 32, 512), (3, 8, 777)])
+def test_non_finite_patches_take_unit_zero_and_leave_their_neighbours_alone(fmaps, p, k):
+    """Non-finite input (a diverged encoder).  The reference's distance row of a patch that holds a NaN is all
+    NaN and torch.argmin returns its first position, unit 0 (models/Codebook.py:86-94; the training loop then
+    stops on its NaN-loss guard, train_codebook.py:237-238).  Every kernel mode must return 0 for such a patch
+    as well, an in-range index for a patch that holds +-inf (the reference's own pick there depends on which
+    inf - inf of its sgemm turns into NaN first), and exactly the clean-run index for every other patch, also
+    for the rows that share a 128-row MMA tile with a poisoned one.  Shapes: config S, resident-A, unit split,
+    streamed, streamed with a large codebook, split-K, ragged."""
+    pd = (p, p)
+    d = 4 * p * p
+    x = synthetic_fmaps(fmaps, 23)
+    w = trained_like_codebook(k, pd, 5)
+    seq = (32 // p) ** 2
+    n = fmaps * seq
+    g = torch.Generator().manual_seed(n + k)
+    poisoned = torch.randperm(n, generator=g)[:max(3, min(48, n // 8))]
+    kinds = [float("nan"), float("inf"), float("-inf")]
+    xp = x.clone()
+    for t, pi in enumerate(poisoned.tolist()):
+        img, s = divmod(pi, seq)
+        ph, pw = divmod(s, 32 // p)
+        f = int(torch.randint(0, d, (1,), generator=g))
+        c, r = divmod(f, p * p)
+        i, j = divmod(r, p)
+        xp[img, c, ph * p + i, pw * p + j] = kinds[t % 3]
+    nan_rows = poisoned[0::3]
+    clean = torch.ones(n, dtype=torch.bool)
+    clean[poisoned] = False
+    oc = make_oracle_codebook(w, pd, (32, 32), 4, k // 2)
+    with torch.no_grad():
+        ref = oc.get_patches_bmu(xp[:min(fmaps, max(8, 2048 // seq))])
+    m = ref.numel()
+    assert bool((ref[nan_rows[nan_rows < m]] == 0).all()), "the oracle itself does not send NaN patches to unit 0"
+    for variant in _variants(n, d, k):
+        cb = _gpu_cb(w, pd, (32, 32), 4, k // 2, variant)
+        base = cb.get_patches_bmu(x.to(DEV)).cpu()
+        idx = cb.get_patches_bmu(xp.to(DEV)).cpu()
+        assert int(idx.min()) >= 0 and int(idx.max()) < k, f"variant {variant}: index outside [0, K)"
+        assert bool((idx[nan_rows] == 0).all()), f"variant {variant}: NaN patch not at unit 0: {idx[nan_rows]}"
+        assert torch.equal(idx[clean], base[clean]), f"variant {variant}: a poisoned row leaked into its neighbours"
+        same = (idx[:m] == ref)[clean[:m]]
+        assert float(same.float().mean()) > 0.999
