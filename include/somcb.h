@@ -17,7 +17,14 @@
  *   - patch geometry (n_img, C, H, Wd, pH, pW) describes an fp32 contiguous NCHW batch that is
  *     cut into (H/pH)*(Wd/pW) patches per image, patch s = ph*(Wd/pW)+pw, feature
  *     d = c*pH*pW + i*pW + j  <->  x[n, c, ph*pH+i, pw*pW+j]   (models/layers.py:8-34).
- *     A pre-flattened (n, D) row matrix is the geometry (n, 1, 1, D, 1, D).
+ *     A pre-flattened (n, D) row matrix is the geometry (n, 1, 1, D, 1, D);
+ *   - a zero count (n_img == 0 / n == 0) is a successful no-op and is the only case in which the
+ *     per-item input/output pointers may be NULL (torch gives zero-element tensors a null
+ *     data pointer); the reference returns empty tensors there (models/Codebook.py:77-99);
+ *   - non-finite input: a patch that holds a NaN gets unit 0 of the searched range, as
+ *     torch.argmin over the reference's all-NaN distance row does; a patch that holds +-inf gets
+ *     some in-range index (the reference's pick there is an accident of its sgemm's inf - inf);
+ *     other patches are unaffected.
  */
 #ifndef SOMCB_H_
 #define SOMCB_H_

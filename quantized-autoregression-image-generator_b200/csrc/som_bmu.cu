@@ -42,12 +42,15 @@ extern "C" int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int
                                 const float* W, const float* c_norm2, int K, int64_t unit_offset,
                                 int64_t* out_idx, float* out_rd,
                                 void* ws, size_t ws_bytes, int variant, void* stream) {
-    SOM_REQUIRE(x && W && c_norm2 && out_idx, SOM_E_BADARG, "bmu: null pointer");
+    // an empty batch (torch hands out null data pointers for zero-element tensors) is a valid no-op: the reference
+    // returns an empty int64 tensor for it (models/Codebook.py:77-99 on a (0, C, H, W) input)
+    SOM_REQUIRE(W && c_norm2 && ((x && out_idx) || n_img == 0), SOM_E_BADARG, "bmu: null pointer");
     SOM_REQUIRE(K > 0, SOM_E_BADARG, "bmu: K=%d", K);
     SOM_REQUIRE(variant >= SOM_BMU_AUTO && variant <= SOM_BMU_TC3X, SOM_E_BADARG, "bmu: variant=%d", variant);
     Geom g;
     int rc = make_geom(&g, x, n_img, C, H, Wd, pH, pW);
     if (rc) return rc;
+    if (g.n_patches == 0) return SOM_OK;
     if (variant == SOM_BMU_AUTO) variant = som_bmu_pick_variant(g.n_patches, g.D, K);
     if (variant == SOM_BMU_TC3X) {
         SOM_REQUIRE(tc_supported(g.n_patches, g.D, K), SOM_E_UNSUPPORTED,

@@ -595,7 +595,7 @@ int som_merge_candidates(const float* rd, const int64_t* idx, int R, int64_t n,
 }
 
 int som_histogram_i64(const int64_t* idx, int64_t n, int K, int64_t* counts, void* stream) {
-    SOM_REQUIRE(idx && counts, SOM_E_BADARG, "histogram: null pointer");
+    SOM_REQUIRE(counts && (idx || n == 0), SOM_E_BADARG, "histogram: null pointer");
     SOM_REQUIRE(K > 0 && n >= 0, SOM_E_BADARG, "histogram: K=%d n=%lld", K, (long long)n);
     if (n == 0) return SOM_OK;
     auto* c = reinterpret_cast<unsigned long long*>(counts);
@@ -639,7 +639,7 @@ int som_histogram_i64(const int64_t* idx, int64_t n, int K, int64_t* counts, voi
 int som_quantize_nchw_f32(const int64_t* idx, const float* table, int K,
                           int64_t n_img, int C, int H, int Wd, int pH, int pW,
                           float* out, void* stream) {
-    SOM_REQUIRE(idx && table && out, SOM_E_BADARG, "quantize: null pointer");
+    SOM_REQUIRE(table && ((idx && out) || n_img == 0), SOM_E_BADARG, "quantize: null pointer");
     SOM_REQUIRE(K > 0, SOM_E_BADARG, "quantize: K=%d", K);
     Geom g;
     int rc = make_geom(&g, out, n_img, C, H, Wd, pH, pW);
@@ -674,8 +674,8 @@ int som_quantize_nchw_f32(const int64_t* idx, const float* table, int K,
 int som_assemble_tokens_i64(const int64_t* lr_idx, const int64_t* hr_idx, int64_t n, int lr_seq, int hr_seq,
                             int64_t lr_K, int64_t hr_K, int base_model, int64_t* hr_input, int64_t* hr_target,
                             void* stream) {
-    SOM_REQUIRE(hr_idx && hr_input && hr_target, SOM_E_BADARG, "assemble_tokens: null pointer");
-    SOM_REQUIRE(!base_model || lr_idx, SOM_E_BADARG, "assemble_tokens: base model needs lr_idx");
+    SOM_REQUIRE((hr_idx && hr_input && hr_target) || n == 0, SOM_E_BADARG, "assemble_tokens: null pointer");
+    SOM_REQUIRE(!base_model || lr_idx || n == 0, SOM_E_BADARG, "assemble_tokens: base model needs lr_idx");
     SOM_REQUIRE(n >= 0 && hr_seq > 0 && lr_seq >= 0, SOM_E_BADARG, "assemble_tokens: n=%lld lr_seq=%d hr_seq=%d",
                 (long long)n, lr_seq, hr_seq);
     if (n == 0) return SOM_OK;

@@ -99,7 +99,8 @@ class Codebook(nn.Module):
         x, geom = self._input(x)
         idx = ops.bmu(x, geom, self._weight(), self._norms(), variant=self.bmu_variant)
         if reshape:
-            idx = idx.reshape(x.shape[0], -1)
+            # explicit Seq, not -1: an empty batch gives (0, Seq) as the reference does
+            idx = idx.reshape(x.shape[0], (geom[2] // geom[4]) * (geom[3] // geom[5]))
         return idx
 
     def get_quantized_patches(self, x, use_gaussian=True):

@@ -408,3 +408,35 @@ def test_filter_ws_entry_point_contract():
     assert lib.som_filter_ws_f32(w.data_ptr(), w.data_ptr(), 4096, 64, 2048.0, 1.0, ws.data_ptr(), need, st) == -1
     assert lib.som_filter_ws_f32(None, a.data_ptr(), 4096, 64, 2048.0, 1.0, ws.data_ptr(), need, st) == -1
     assert lib.som_filter_ws_f32(w.data_ptr(), a.data_ptr(), 4096, 64, -1.0, 1.0, ws.data_ptr(), need, st) == -1
+
+
+def test_empty_batch_is_a_no_op_with_the_reference_shapes():
+    """A (0, C, H, W) batch: the reference returns an empty int64 index tensor ((0,) and (0, Seq) reshaped,
+    models/Codebook.py:77-99) and an empty image batch from get_quantized_image (:138-154).  torch hands out
+    null data pointers for zero-element tensors; the C-ABI accepts them when the count is zero."""
+    w = trained_like_codebook(256, (4, 4), 3)
+    cb = somcb.Codebook(patch_dim=(4, 4), image_dim=(32, 32), image_channel=4, num_embeddings=256,
+                        init_neighbour_range=128)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(w)
+    cb = cb.to(DEV)
+    x = torch.zeros(0, 4, 32, 32, device=DEV)
+    for variant in (ops.SOM_BMU_AUTO, ops.SOM_BMU_FFMA, ops.SOM_BMU_TC3X):
+        cb.bmu_variant = variant
+        idx = cb.get_patches_bmu(x)
+        assert idx.dtype == torch.int64 and tuple(idx.shape) == (0,)
+        assert tuple(cb.get_patches_bmu(x, reshape=True).shape) == (0, 64)
+    img = cb.get_quantized_image(torch.zeros(0, 64, dtype=torch.int64, device=DEV))
+    assert tuple(img.shape) == (0, 4, 32, 32)
+    counts = ops.histogram(torch.zeros(0, dtype=torch.int64, device=DEV), 256)
+    assert int(counts.sum()) == 0
+    # the raw entry points: null data pointers are only accepted together with a zero count
+    lib = _lib.load()
+    cn = ops.prepare_codebook(cb.codebook.weight.detach())
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.som_bmu_nchw_f32(None, 0, 4, 32, 32, 4, 4, cb.codebook.weight.data_ptr(), cn.data_ptr(), 256, 0,
+                              None, None, None, 0, ops.SOM_BMU_AUTO, st)
+    assert rc == 0
+    rc = lib.som_bmu_nchw_f32(None, 1, 4, 32, 32, 4, 4, cb.codebook.weight.data_ptr(), cn.data_ptr(), 256, 0,
+                              None, None, None, 0, ops.SOM_BMU_AUTO, st)
+    assert rc == -1 and b"null pointer" in lib.som_last_error()
