@@ -54,12 +54,6 @@ class SomTrainer:
         self.use_cuda_graph = bool(use_cuda_graph) and reduce_fn is None
         self._graph_alias = use_cuda_graph == "alias"
         self._graph = None            # (key, CUDAGraph, x_static, loss_static, t_dev)
-        # W~ = T @ W depends on W only, like the BMU search: it runs on a side stream next to the codebook
-        # preparation + BMU kernels and joins before the accumulation (a fork / join inside the captured graph
-        # as well).  SOM_TRAINER_FORK=0 keeps the step on one stream (A/B timing).
-        import os
-        self._fork = w.is_cuda and os.environ.get("SOM_TRAINER_FORK", "1") != "0"
-        self._side = None
 
     @torch.no_grad()
     def step(self, feature_map, bmu=None):
@@ -109,21 +103,9 @@ class SomTrainer:
         k = cb.num_embeddings
         rng = cb.neighbourhood_range
 
-        fork = self._fork and bmu is None and x.is_cuda
-        if fork:
-            if self._side is None or self._side.device != x.device:
-                self._side = torch.cuda.Stream(device=x.device)
-            main = torch.cuda.current_stream(x.device)
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                wt = ops.neighbourhood_filter(w, rng)
-        else:
-            wt = ops.neighbourhood_filter(w, rng)
+        wt = ops.neighbourhood_filter(w, rng)
         if bmu is None:
             bmu = ops.bmu(x, geom, w, ops.prepare_codebook(w), variant=cb.bmu_variant)
-        if fork:
-            main.wait_stream(self._side)
-            wt.record_stream(main)
         numel = x.numel() * self.world_size            # every rank holds an equal share
         if self.reduce_fn is None:
             rbar, _, sse = ops.accumulate(x, geom, bmu, wt, k, want_sse=True)
