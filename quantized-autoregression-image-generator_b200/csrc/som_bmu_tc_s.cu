@@ -30,6 +30,7 @@
 #include "som_common.cuh"
 #include "som_tc_ptx.cuh"
 
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace som {
@@ -89,6 +90,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
 
 __device__ long long g_prof[4];              // CTA 0: cycles of the MMA loop, tiles issued
 
+// eight halves (one 16-byte swizzle chunk) from eight floats, round-to-nearest-even
+__device__ __forceinline__ uint4 pack_h8(const float (&v)[8]) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    return make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                      *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+}
+
+// F16 = true: the same pipeline with a two-way FP16 split instead of the TF32 one (kind::f16 MMAs have K = 16 at the
+// cycle cost of a K = 8 TF32 MMA: a tile is 4 MMAs instead of 7).  Rows are scaled by exact powers of two so that the
+// halves stay in FP16's normal range -- per patch (s_p, chosen from max |x|) and per codebook (s_c, from max |c| and
+// max ||c||^2) -- and one 128-byte row carries everything:
+//     A row = [ hi(s_p x) (16) | lo(s_p x) (16) | s_p s_p s_p 0.. (16) | unused ]
+//     B row = [ hi(-2 s_c c) (16) | lo(-2 s_c c) (16) | n1 n2 n3 0.. (16) of s_c ||c||^2 | unused ]
+// so the accumulator holds s_p s_c rd: a positive factor per row, which the argmin over units does not see.  The
+// winning chunk is still resolved with exact fp32 FFMA scores of the unscaled operands.
+template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
     extern __shared__ uint8_t smem_raw[];
@@ -111,7 +129,12 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int d = threadIdx.x; d < P.g.D; d += NUM_THREADS) aux.foff[d] = feat_off(P.g, d);
-    if (threadIdx.x < TM) {
+    if (F16) {
+        // chunks 5..7 of every A row are never written by the builders and chunk 5 is read by the tail k-step
+        for (int i = threadIdx.x; i < R * A_BLK_BYTES / 16; i += NUM_THREADS)
+            reinterpret_cast<uint4*>(a_slots)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    } else if (threadIdx.x < TM) {
         // constant tail operand: row t = [1 1 1 0 | 0 0 0 0] in the 32-byte swizzle (chunk ^= bit 2 of t)
         const int t = threadIdx.x;
         const uint32_t sw = (uint32_t)(t >> 2) & 1u;
@@ -142,9 +165,9 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 for (int n = 0; n < P.NT; ++n) {
                     mbar_wait(&bars.empty[stage], phase ^ 1);
                     uint8_t* sbase = ring + (size_t)stage * STAGE_BYTES;
-                    mbar_expect_tx(&bars.full[stage], STAGE_BYTES);
+                    mbar_expect_tx(&bars.full[stage], F16 ? B_BLK_BYTES : STAGE_BYTES);
                     tma_load_2d(&map_b, &bars.full[stage], sbase, 0, n * TN);
-                    tma_load_2d(&map_t, &bars.full[stage], sbase + B_BLK_BYTES, 0, n * TN);
+                    if (!F16) tma_load_2d(&map_t, &bars.full[stage], sbase + B_BLK_BYTES, 0, n * TN);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
@@ -177,7 +200,17 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     tc_fence_after();
                     const uint32_t d_addr = tmem_base + (j & 1u) * TN;
                     const uint64_t ad = adesc0 + (uint32_t)r * SLOT_UNITS;
-                    if (leader) {
+                    if (F16) {
+                        if (leader) {
+                            // norm tail (k-step 2 of both rows) first, then hi.hi, lo.hi, hi.lo
+                            tc_mma_f16(d_addr, ad + 4u, bd + 4u, 0u);
+                            tc_mma_f16(d_addr, ad, bd, 1u);
+                            tc_mma_f16(d_addr, ad + 2u, bd, 1u);
+                            tc_mma_f16(d_addr, ad, bd + 2u, 1u);
+                            tc_commit(&bars.acc_full[j & 1u]);
+                            if (n == P.NT - 1) tc_commit(&bars.a_empty[r]);
+                        }
+                    } else if (leader) {
                         // norm tail first, then hi.hi, lo.hi, hi.lo
                         tc_mma_tf32(d_addr, atdesc, btd, 0u);
 #pragma unroll
@@ -285,7 +318,35 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 if (r < r_eff) {
                     mbar_wait_warp<true>(&bars.a_empty[r], a_epar, lane);
                     uint8_t* slot = a_slots + (size_t)r * A_BLK_BYTES + row_off;
-                    if (v4) {
+                    if (F16) {
+                        // power-of-two row scale: max |s_p x| in [64, 128), s_p itself an FP16 normal (2^-14 .. 2^15);
+                        // an all-zero or non-finite row keeps s_p = 1
+                        float m = 0.f;
+#pragma unroll
+                        for (int d = 0; d < DMAX; ++d) m = fmaxf(m, fabsf(xv[r][d]));
+                        const int eb = (int)((__float_as_uint(m) >> 23) & 0xffu);
+                        int ep = 133 - eb;
+                        ep = ep > 15 ? 15 : (ep < -14 ? -14 : ep);
+                        if (!(m > 0.f) || eb == 0xff) ep = 0;
+                        const float sp = __uint_as_float((uint32_t)(127 + ep) << 23);
+                        float hi[DMAX], lo[DMAX];
+#pragma unroll
+                        for (int d = 0; d < DMAX; ++d) {
+                            const float v = xv[r][d] * sp;              // exact
+                            hi[d] = __half2float(__float2half_rn(v));
+                            lo[d] = v - hi[d];                          // exact; rounded to FP16 when packed
+                        }
+                        const float h0[8] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]};
+                        const float h1[8] = {hi[8], hi[9], hi[10], hi[11], hi[12], hi[13], hi[14], hi[15]};
+                        const float l0[8] = {lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]};
+                        const float l1[8] = {lo[8], lo[9], lo[10], lo[11], lo[12], lo[13], lo[14], lo[15]};
+                        const float tl[8] = {sp, sp, sp, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        *reinterpret_cast<uint4*>(slot + ((0u ^ sw) << 4)) = pack_h8(h0);
+                        *reinterpret_cast<uint4*>(slot + ((1u ^ sw) << 4)) = pack_h8(h1);
+                        *reinterpret_cast<uint4*>(slot + ((2u ^ sw) << 4)) = pack_h8(l0);
+                        *reinterpret_cast<uint4*>(slot + ((3u ^ sw) << 4)) = pack_h8(l1);
+                        *reinterpret_cast<uint4*>(slot + ((4u ^ sw) << 4)) = pack_h8(tl);
+                    } else if (v4) {
                         // 16-byte chunk q of the row lands at (q ^ (t & 7)): 8 consecutive rows fill one
                         // conflict-free shared-memory wavefront
                         const int dq = Dp >> 2;
@@ -453,6 +514,64 @@ __global__ void __launch_bounds__(256) split_w_s_kernel(const float* __restrict_
     }
 }
 
+// FP16 mode, per-codebook scale s_c = 2^e: max |s_c c| in [64, 128) unless that would push max s_c ||c||^2 to 2^15 or
+// beyond (FP16 tops out at 65504); an all-zero or non-finite codebook keeps s_c = 1.  One CTA: the config-S codebooks
+// are K x (D <= 16) floats.
+__global__ void __launch_bounds__(1024) cb_scale_kernel(const float* __restrict__ W, const float* __restrict__ cn,
+                                                        int K, int D, float* __restrict__ scale_out) {
+    __shared__ float sh_c[32], sh_n[32];
+    float mc = 0.f, mn = 0.f;
+    const int64_t total = (int64_t)K * D;
+    for (int64_t i = threadIdx.x; i < total; i += 1024) mc = fmaxf(mc, fabsf(W[i]));
+    for (int i = threadIdx.x; i < K; i += 1024) mn = fmaxf(mn, fabsf(cn[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+        mn = fmaxf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) { sh_c[threadIdx.x >> 5] = mc; sh_n[threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { mc = fmaxf(mc, sh_c[w]); mn = fmaxf(mn, sh_n[w]); }
+        const int ec = (int)((__float_as_uint(mc) >> 23) & 0xffu), en = (int)((__float_as_uint(mn) >> 23) & 0xffu);
+        int e = 0;
+        if (mc > 0.f && ec != 0xff && en != 0xff) {
+            e = 133 - ec;                                   // max |s_c c| in [64, 128)
+            if (mn > 0.f) { const int e2 = 141 - en; e = e < e2 ? e : e2; }     // max s_c ||c||^2 in [2^14, 2^15)
+            e = e > 100 ? 100 : (e < -100 ? -100 : e);
+        }
+        *scale_out = __uint_as_float((uint32_t)(127 + e) << 23);
+    }
+}
+
+// FP16 mode B rows: 64 halves = [ hi(-2 s_c c) (16) | lo (16) | n1 n2 n3 0.. (16) of s_c ||c||^2 | 0 (16) ].  Rows >= K
+// repeat unit K - 1: a padding unit then never beats a real one (ties go to the lower chunk), whatever the patch holds.
+__global__ void __launch_bounds__(256) split_w_s16_kernel(const float* __restrict__ W, const float* __restrict__ cn,
+                                                          int K, int D, int K_pad, const float* __restrict__ scale,
+                                                          __half* __restrict__ Bp) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)K_pad * 64) return;
+    const int row = (int)(t >> 6);
+    const int c = (int)(t & 63);
+    const int src = row < K ? row : K - 1;
+    const float sc = *scale;
+    float out = 0.f;
+    if (c < 32) {
+        const int d = c & 15;
+        if (d < D) {
+            const float v = -2.0f * sc * W[(int64_t)src * D + d];          // exact scaling
+            const float hi = __half2float(__float2half_rn(v));
+            out = (c < 16) ? hi : v - hi;
+        }
+    } else if (c < 35) {
+        const float nrm = cn[src] * sc;
+        const float n1 = __half2float(__float2half_rn(nrm));
+        const float n2 = __half2float(__float2half_rn(nrm - n1));
+        out = (c == 32) ? n1 : (c == 33) ? n2 : (nrm - n1 - n2);
+    }
+    Bp[(int64_t)row * 64 + c] = __float2half_rn(out);
+}
+
 }  // namespace tcs
 
 bool tc_s_applicable(int D) { return D >= 1 && D <= tcs::DMAX; }
@@ -460,7 +579,14 @@ bool tc_s_applicable(int D) { return D >= 1 && D <= tcs::DMAX; }
 size_t tc_s_workspace_bytes(int64_t n_patches, int D, int K) {
     (void)n_patches; (void)D;
     const size_t K_pad = (size_t)(K + tc::TN - 1) / tc::TN * tc::TN;
-    return align_up(K_pad * 32 * 4, 1024) + align_up(K_pad * 8 * 4, 1024);
+    return align_up(K_pad * 32 * 4, 1024) + align_up(K_pad * 8 * 4, 1024) + 1024;     // + the FP16 mode's scale slot
+}
+
+// FP16-split mode of the config-S kernel (default) or the 3xTF32 one: SOM_TC_S_F16=0 / 1, read once per process
+static bool tc_s_f16_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("SOM_TC_S_F16"); mode = e ? (atoi(e) != 0) : 0; }
+    return mode != 0;
 }
 
 int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
@@ -476,7 +602,17 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
     SOM_REQUIRE(((uintptr_t)ws & 255) == 0, SOM_E_BADARG, "bmu(tc): workspace must be 256-byte aligned");
     float* Bp = (float*)ws;
     float* Tp = (float*)((char*)ws + align_up((size_t)K_pad * 32 * 4, 1024));
-    {
+    float* scale = (float*)((char*)Tp + align_up((size_t)K_pad * 8 * 4, 1024));
+    const bool f16 = tc_s_f16_mode();
+    if (f16) {
+        cb_scale_kernel<<<1, 1024, 0, st>>>(W, cn, K, D, scale);
+        int rc = check_launch("cb_scale_kernel");
+        if (rc) return rc;
+        const int64_t items = (int64_t)K_pad * 64;
+        split_w_s16_kernel<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(W, cn, K, D, K_pad, scale, (__half*)Bp);
+        rc = check_launch("split_w_s16_kernel");
+        if (rc) return rc;
+    } else {
         const int64_t items = (int64_t)K_pad * 40;
         split_w_s_kernel<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(W, cn, K, D, Dp, K_pad, Bp, Tp);
         int rc = check_launch("split_w_s_kernel");
@@ -499,7 +635,9 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
 #endif
     static PerDeviceFlag attr_done;
     if (attr_done.pending()) {
-        cudaError_t e = cudaFuncSetAttribute(bmu_tc_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(bmu_tc_s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(bmu_tc_s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { set_error("bmu(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done.set();
     }
@@ -509,7 +647,8 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
     P.Rr = rr < 1 ? 1 : (rr > R ? R : rr);
     const int n_super = (P.n_mtiles + P.Rr - 1) / P.Rr;
     const int grid = n_super < sm_count() ? n_super : sm_count();
-    bmu_tc_s_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
+    if (f16) bmu_tc_s_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
+    else bmu_tc_s_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_b, map_t, P);
     return check_launch("bmu_tc_s_kernel");
 }
 

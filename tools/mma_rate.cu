@@ -510,37 +510,44 @@ __global__ void __launch_bounds__(1024) ffma_peak_kernel(float* out, int iters) 
     if (s == 123.456f) out[threadIdx.x] = s;
 }
 
+template <int MODE>
+static void sustained_tc(const char* name, int kdepth) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = 148, kblocks = 2, iters = 600000;     // 4.8 M MMAs per CTA
+    long long* out; long long* fb; uint8_t* src;
+    cudaMalloc(&out, grid * sizeof(long long)); cudaMalloc(&fb, grid * sizeof(long long)); cudaMalloc(&src, 8 * 131072);
+    const int smem = 1024 + kblocks * (128 * 128 + 256 * 128) + 32768;
+    cudaFuncSetAttribute(rate_kernel<1, 256, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, rate_kernel<1, 256, MODE>, 1000, kblocks, out, (const uint8_t*)src, fb);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    cudaLaunchKernelEx(&cfg, rate_kernel<1, 256, MODE>, iters, kblocks, out, (const uint8_t*)src, fb);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    const double n_mma = (double)iters * kblocks * 4;
+    const double tf = 148.0 * n_mma * 128 * 256 * kdepth * 2 / (ms * 1e-3) / 1e12;
+    printf("SUSTAINED %s tcgen05 (random operands): %.1f ms, %.1f TFLOP/s dense -> %.1f TFLOP/s fp32-faithful (3 products), "
+           "%.1f cycles/MMA, average SM clock %.3f GHz  [%s]\n", name, ms, tf, tf / 3.0, (double)h[0] / n_mma,
+           (double)h[0] / (ms * 1e-3) / 1e9, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    cudaFree(out); cudaFree(fb); cudaFree(src);
+}
+
 static void run_sustained() {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    // TF32 tensor pipe: ~0.6 s of back-to-back M128 N256 K8 MMAs on every SM
-    {
-        const int grid = 148, kblocks = 2, iters = 600000;     // 4.8 M MMAs per CTA
-        long long* out; long long* fb; uint8_t* src;
-        cudaMalloc(&out, grid * sizeof(long long)); cudaMalloc(&fb, grid * sizeof(long long)); cudaMalloc(&src, 8 * 131072);
-        const int smem = 1024 + kblocks * (128 * 128 + 256 * 128) + 32768;
-        cudaFuncSetAttribute(rate_kernel<1, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, rate_kernel<1, 256, 32>, 1000, kblocks, out, (const uint8_t*)src, fb);
-        cudaDeviceSynchronize();
-        cudaEventRecord(e0);
-        cudaLaunchKernelEx(&cfg, rate_kernel<1, 256, 32>, iters, kblocks, out, (const uint8_t*)src, fb);
-        cudaEventRecord(e1);
-        cudaError_t e = cudaDeviceSynchronize();
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-        long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
-        const double n_mma = (double)iters * kblocks * 4;
-        const double tf = 148.0 * n_mma * 128 * 256 * 8 * 2 / (ms * 1e-3) / 1e12;
-        printf("SUSTAINED tf32 tcgen05 (random operands): %.1f ms, %.1f TFLOP/s dense TF32 -> %.1f TFLOP/s fp32-faithful (3 products), "
-               "%.1f cycles/MMA, average SM clock %.3f GHz  [%s]\n", ms, tf, tf / 3.0, (double)h[0] / n_mma,
-               (double)h[0] / (ms * 1e-3) / 1e9, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
-        cudaFree(out); cudaFree(fb); cudaFree(src);
-    }
+    // tensor pipe: ~0.4-0.6 s of back-to-back M128 N256 MMAs on every SM, kind::tf32 (K = 8) then kind::f16 with bf16
+    // operands (K = 16): the second line is what a two-way 16-bit split (3 products at twice the rate) would run at
+    sustained_tc<32>("tf32", 8);
+    sustained_tc<34>("f16 kind (bf16 operands)", 16);
     // FP32 FFMA: 148 x 2 CTAs x 1024 threads, 64 independent FMAs per iteration
     {
         float* out; cudaMalloc(&out, 4096);
