@@ -64,6 +64,7 @@ struct Params {
     const float* cn;
     int K;
     int dbg;                // timing-elimination switches, 0 unless built with -DSOM_TC_EXPERIMENTS
+    const float* scale;     // FP16 mode: [s_c, t_c] written by cb_scale_kernel earlier on the stream
 };
 
 struct __align__(8) Barriers {
@@ -100,10 +101,11 @@ __device__ __forceinline__ uint4 pack_h8(const float (&v)[8]) {
 
 // F16 = true: the same pipeline with a two-way FP16 split instead of the TF32 one (kind::f16 MMAs have K = 16 at the
 // cycle cost of a K = 8 TF32 MMA: a tile is 4 MMAs instead of 7).  Rows are scaled by exact powers of two so that the
-// halves stay in FP16's normal range -- per patch (s_p, chosen from max |x|) and per codebook (s_c, from max |c| and
-// max ||c||^2) -- and one 128-byte row carries everything:
-//     A row = [ hi(s_p x) (16) | lo(s_p x) (16) | s_p s_p s_p 0.. (16) | unused ]
-//     B row = [ hi(-2 s_c c) (16) | lo(-2 s_c c) (16) | n1 n2 n3 0.. (16) of s_c ||c||^2 | unused ]
+// halves stay in FP16's normal range -- per patch (s_p, from max |x|), per codebook (s_c, from max |c|) and, for the
+// norm column, t_c (from max s_c ||c||^2; the norms are quadratic in the codebook's magnitude, the products are not) --
+// and one 128-byte row carries everything:
+//     A row = [ hi(s_p x) (16) | lo(s_p x) (16) | a_p a_p a_p 0.. (16) | unused ]                  a_p = s_p / t_c
+//     B row = [ hi(-2 s_c c) (16) | lo(-2 s_c c) (16) | n1 n2 n3 0.. (16) of t_c s_c ||c||^2 | unused ]
 // so the accumulator holds s_p s_c rd: a positive factor per row, which the argmin over units does not see.  The
 // winning chunk is still resolved with exact fp32 FFMA scores of the unscaled operands.
 template <bool F16>
@@ -243,6 +245,7 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         const uint32_t sw = (uint32_t)(t & 7);
         const bool v4 = ((D & 3) == 0);
         const bool w4 = v4 && ((reinterpret_cast<uintptr_t>(P.W) & 15) == 0);
+        const int tc_exp = F16 ? (int)((__float_as_uint(__ldg(P.scale + 1)) >> 23) & 0xffu) - 127 : 0;
         float xv[R][DMAX];
         auto prefetch = [&](int st_next) {
             const int r_nxt = (st_next < n_super) ? min(Rr, P.n_mtiles - st_next * Rr) : 0;
@@ -319,16 +322,21 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     mbar_wait_warp<true>(&bars.a_empty[r], a_epar, lane);
                     uint8_t* slot = a_slots + (size_t)r * A_BLK_BYTES + row_off;
                     if (F16) {
-                        // power-of-two row scale: max |s_p x| in [64, 128), s_p itself an FP16 normal (2^-14 .. 2^15);
-                        // an all-zero or non-finite row keeps s_p = 1
+                        // power-of-two row scale: max |s_p x| in [64, 128) as long as a_p = s_p / t_c stays an FP16
+                        // normal (2^-14 .. 2^15; beyond that the row moves away from the ideal range binade by binade);
+                        // an all-zero or non-finite row takes the ideal exponent 0
                         float m = 0.f;
 #pragma unroll
                         for (int d = 0; d < DMAX; ++d) m = fmaxf(m, fabsf(xv[r][d]));
                         const int eb = (int)((__float_as_uint(m) >> 23) & 0xffu);
                         int ep = 133 - eb;
-                        ep = ep > 15 ? 15 : (ep < -14 ? -14 : ep);
                         if (!(m > 0.f) || eb == 0xff) ep = 0;
-                        const float sp = __uint_as_float((uint32_t)(127 + ep) << 23);
+                        int ka = ep - tc_exp;
+                        ka = ka > 15 ? 15 : (ka < -14 ? -14 : ka);
+                        int es = ka + tc_exp;
+                        es = es > 120 ? 120 : (es < -120 ? -120 : es);
+                        const float sp = __uint_as_float((uint32_t)(127 + es) << 23);
+                        const float ap = __uint_as_float((uint32_t)(127 + ka) << 23);
                         float hi[DMAX], lo[DMAX];
 #pragma unroll
                         for (int d = 0; d < DMAX; ++d) {
@@ -340,7 +348,7 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                         const float h1[8] = {hi[8], hi[9], hi[10], hi[11], hi[12], hi[13], hi[14], hi[15]};
                         const float l0[8] = {lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]};
                         const float l1[8] = {lo[8], lo[9], lo[10], lo[11], lo[12], lo[13], lo[14], lo[15]};
-                        const float tl[8] = {sp, sp, sp, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        const float tl[8] = {ap, ap, ap, 0.f, 0.f, 0.f, 0.f, 0.f};
                         *reinterpret_cast<uint4*>(slot + ((0u ^ sw) << 4)) = pack_h8(h0);
                         *reinterpret_cast<uint4*>(slot + ((1u ^ sw) << 4)) = pack_h8(h1);
                         *reinterpret_cast<uint4*>(slot + ((2u ^ sw) << 4)) = pack_h8(l0);
@@ -514,9 +522,9 @@ __global__ void __launch_bounds__(256) split_w_s_kernel(const float* __restrict_
     }
 }
 
-// FP16 mode, per-codebook scale s_c = 2^e: max |s_c c| in [64, 128) unless that would push max s_c ||c||^2 to 2^15 or
-// beyond (FP16 tops out at 65504); an all-zero or non-finite codebook keeps s_c = 1.  One CTA: the config-S codebooks
-// are K x (D <= 16) floats.
+// FP16 mode, per-codebook scales (powers of two): s_c puts max |s_c c| in [64, 128), t_c puts max t_c s_c ||c||^2 in
+// [2^14, 2^15) (FP16 tops out at 65504); an all-zero or non-finite codebook keeps both at 1.  One CTA: the config-S
+// codebooks are K x (D <= 16) floats.
 __global__ void __launch_bounds__(1024) cb_scale_kernel(const float* __restrict__ W, const float* __restrict__ cn,
                                                         int K, int D, float* __restrict__ scale_out) {
     __shared__ float sh_c[32], sh_n[32];
@@ -534,13 +542,17 @@ __global__ void __launch_bounds__(1024) cb_scale_kernel(const float* __restrict_
     if (threadIdx.x == 0) {
         for (int w = 1; w < 32; ++w) { mc = fmaxf(mc, sh_c[w]); mn = fmaxf(mn, sh_n[w]); }
         const int ec = (int)((__float_as_uint(mc) >> 23) & 0xffu), en = (int)((__float_as_uint(mn) >> 23) & 0xffu);
-        int e = 0;
+        int e = 0, g = 0;
         if (mc > 0.f && ec != 0xff && en != 0xff) {
             e = 133 - ec;                                   // max |s_c c| in [64, 128)
-            if (mn > 0.f) { const int e2 = 141 - en; e = e < e2 ? e : e2; }     // max s_c ||c||^2 in [2^14, 2^15)
-            e = e > 100 ? 100 : (e < -100 ? -100 : e);
+            e = e > 60 ? 60 : (e < -60 ? -60 : e);
+            const float msn = mn * __uint_as_float((uint32_t)(127 + e) << 23);
+            const int es = (int)((__float_as_uint(msn) >> 23) & 0xffu);
+            if (msn > 0.f && es != 0xff) g = 141 - es;     // max t_c s_c ||c||^2 in [2^14, 2^15)
+            g = g > 60 ? 60 : (g < -60 ? -60 : g);
         }
-        *scale_out = __uint_as_float((uint32_t)(127 + e) << 23);
+        scale_out[0] = __uint_as_float((uint32_t)(127 + e) << 23);
+        scale_out[1] = __uint_as_float((uint32_t)(127 + g) << 23);
     }
 }
 
@@ -554,7 +566,7 @@ __global__ void __launch_bounds__(256) split_w_s16_kernel(const float* __restric
     const int row = (int)(t >> 6);
     const int c = (int)(t & 63);
     const int src = row < K ? row : K - 1;
-    const float sc = *scale;
+    const float sc = scale[0], tcs = scale[1];
     float out = 0.f;
     if (c < 32) {
         const int d = c & 15;
@@ -564,7 +576,7 @@ __global__ void __launch_bounds__(256) split_w_s16_kernel(const float* __restric
             out = (c < 16) ? hi : v - hi;
         }
     } else if (c < 35) {
-        const float nrm = cn[src] * sc;
+        const float nrm = cn[src] * sc * tcs;
         const float n1 = __half2float(__float2half_rn(nrm));
         const float n2 = __half2float(__float2half_rn(nrm - n1));
         out = (c == 32) ? n1 : (c == 33) ? n2 : (nrm - n1 - n2);
@@ -627,7 +639,7 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
     Params P;
     P.nks = Dp / 8; P.NT = K_pad / TN; P.n_mtiles = (int)ceil_div64(n, TM); P.rows = n;
     P.unit_offset = unit_offset; P.out_idx = out_idx; P.out_rd = out_rd;
-    P.x = x; P.g = g; P.W = W; P.cn = cn; P.K = K;
+    P.x = x; P.g = g; P.W = W; P.cn = cn; P.K = K; P.scale = scale;
     P.dbg = 0;
 #ifdef SOM_TC_EXPERIMENTS
     // timing-elimination switches (skip refine / loads / conversion): results are wrong, experiment builds only

@@ -22,6 +22,9 @@ if fresh:
     w = torch.empty(k, d).uniform_(-1 / k, 1 / k)
 else:
     w = trained_like_codebook(k, pd, 7)
+scale = float(os.environ.get("SOM_PROBE_SCALE", "1"))      # data and codebook magnitude (exercises the FP16 mode's scaling)
+if scale != 1.0:
+    x, w = x * scale, w * scale
 dev = "cuda:0"
 xd, wd = x.to(dev), w.to(dev)
 geom = ops.geometry(x.shape, pd)

@@ -301,3 +301,26 @@ def test_non_finite_patches_take_unit_zero_and_leave_their_neighbours_alone(fmap
         assert torch.equal(idx[clean], base[clean]), f"variant {variant}: a poisoned row leaked into its neighbours"
         same = (idx[:m] == ref)[clean[:m]]
         assert float(same.float().mean()) > 0.999
+
+
+@pytest.mark.parametrize("mode", ["1", "0"])
+def test_config_s_split_modes_in_a_subprocess(mode):
+    """The config-S kernel (D <= 16) has two operand splits: FP16 (kind::f16, 4 MMAs per tile, per-patch and
+    per-codebook power-of-two scaling) and TF32 (7 MMAs per tile).  SOM_TC_S_F16 is read once per process, so each
+    mode runs the parity probe in its own interpreter: trained-like and fresh codebooks, ragged D, and data / codebook
+    magnitudes from 1e-6 to 1e4 (outside FP16's range without the scaling)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = os.path.join(root, "tests", "tc_probe.py")
+    runs = [(("64", "2", "4096", "2"), "1"), (("64", "2", "4096", "2", "fresh"), "1"), (("48", "2", "777", "2"), "1"),
+            (("64", "2", "4096", "2"), "1e-6"), (("64", "2", "4096", "2"), "1e-3"), (("64", "2", "4096", "2"), "1e4"),
+            (("64", "1", "300", "2"), "1"), (("40", "2", "20000", "2"), "1")]
+    for shp, scale in runs:
+        r = subprocess.run([sys.executable, probe, *shp], capture_output=True, text=True, timeout=300,
+                           env={**os.environ, "SOM_TC_S_F16": mode, "SOM_PROBE_SCALE": scale})
+        assert r.returncode == 0, f"mode {mode} {shp} x{scale}: {r.stdout[-400:]} {r.stderr[-800:]}"
+        assert "OK:" in r.stdout, r.stdout[-400:]
+        if scale == "1" and "fresh" not in shp:
+            assert "OK: 0 near-tie diffs" in r.stdout, r.stdout[-300:]
