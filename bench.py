@@ -375,7 +375,10 @@ def main():
     # ---- roofline of the dominant kernel (BMU) --------------------------------------------------
     flops = 2.0 * k * d_dim * n_p
     achieved = flops / (ms_step * 1e-3) / 1e12
-    tc_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * 0.5 / 3.0
+    # config-S split mode of the library (csrc/som_bmu_tc_s.cu): FP16 hi/lo by default, TF32 with SOM_TC_S_F16=0
+    f16_split = variant == 2 and os.environ.get("SOM_TC_S_F16", "1") != "0"
+    bf16_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    tc_peak = bf16_peak / 3.0 if f16_split else bf16_peak * 0.5 / 3.0
     traffic, pipe_pct = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -394,8 +397,11 @@ def main():
             pipe_peak = json.load(f).get("tf32_3x_fp32_faithful_tflops_sustained")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                 "frac": achieved / tc_peak, "traffic": traffic,
-                "kernel": "bmu_tc3x (tcgen05 kind::tf32 x3)" if variant == 2 else "bmu_ffma (fp32 FFMA)",
-                "peak_basis": f"{peaks['_source']}: sustained bf16 x 1/2 (tf32) x 1/3 (3xTF32, fp32-faithful)",
+                "kernel": ("bmu_tc_s (tcgen05 kind::f16 x3, FP16 hi/lo split)" if f16_split else
+                           "bmu_tc3x (tcgen05 kind::tf32 x3)") if variant == 2 else "bmu_ffma (fp32 FFMA)",
+                "peak_basis": (f"{peaks['_source']}: sustained bf16 x 1/3 (three 16-bit products, fp32-faithful)"
+                               if f16_split else
+                               f"{peaks['_source']}: sustained bf16 x 1/2 (tf32) x 1/3 (3xTF32, fp32-faithful)"),
                 "algorithmic_flops_per_patch": 2 * k * d_dim,
                 "algorithmic_bytes_per_patch": 4 * d_dim + 8,
                 "hbm_frac": (4 * d_dim + 8) * n_p / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
@@ -404,11 +410,16 @@ def main():
                 "frac_of_measured_tcgen05_tf32_peak": (achieved / pipe_peak) if pipe_peak else None,
                 "measured_tcgen05_tf32_peak_3x": pipe_peak,
                 "tensor_pipe_active_pct_ncu": pipe_pct,
-                "note": "frac > 1 is expected: the denominator is the measured sustained cuBLAS bf16 rate / 6; "
-                        "the kernel keeps the tensor pipe ~94% active (ncu) and is bounded by the SM clock "
-                        "under the power cap (1.55-1.65 GHz).  Against the tensor pipe's own measured sustained "
-                        "TF32 rate (930 TFLOP/s dense = 310 fp32-faithful) see frac_of_measured_tcgen05_tf32_peak; "
-                        "7 MMAs per tile carry 6 MMAs of useful products (K' = 56 for 3*16)"}
+                "note": ("FP16-split mode: 4 MMAs (512 tensor-pipe cycles) per 128x256 tile; the pace is set by the "
+                         "epilogue's min-reduction on the half-rate ALU pipe (~850 cycles per tile, 547 with the "
+                         "reduction switched off: DESIGN 5), so frac is against a roof this kernel does not bind on; "
+                         "SOM_TC_S_F16=0 selects the 3xTF32 mode (7 MMAs per tile, tensor pipe 94% active)"
+                         if f16_split else
+                         "frac > 1 is expected: the denominator is the measured sustained cuBLAS bf16 rate / 6; "
+                         "the kernel keeps the tensor pipe ~94% active (ncu) and is bounded by the SM clock "
+                         "under the power cap (1.55-1.65 GHz).  Against the tensor pipe's own measured sustained "
+                         "TF32 rate (930 TFLOP/s dense = 310 fp32-faithful) see frac_of_measured_tcgen05_tf32_peak; "
+                         "7 MMAs per tile carry 6 MMAs of useful products (K' = 56 for 3*16)")}
 
     extra = None
     if not args.no_extra:

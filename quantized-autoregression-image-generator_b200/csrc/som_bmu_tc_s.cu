@@ -1,5 +1,10 @@
 // K1 (tensor-core variant), small patch dimension D <= 16 ("config S"): BMU search as an
-// error-compensated 3xTF32 GEMM on tcgen05 with the argmin fused into the TMEM epilogue.  sm_100a only.
+// error-compensated split GEMM on tcgen05 with the argmin fused into the TMEM epilogue.  sm_100a only.
+// Two operand splits share the pipeline: FP16 hi/lo with power-of-two scaling (default: kind::f16, 4 MMAs per
+// 128 x 256 tile, see the note above the kernel) and TF32 hi/lo (SOM_TC_S_F16=0: kind::tf32, 7 MMAs per tile,
+// described first below).  Measured at C2: 4.1-4.3 ms vs 4.8-4.9 ms per 10 000 128 patches; in the FP16 mode the
+// min-reduction of the epilogue (half-rate FMNMX on the ALU pipe, ~300 cycles per tile) and not the tensor pipe
+// (512 cycles per tile) sets the pace: 850 cycles per tile, 547 with the reduction switched off.
 //
 // Replaces patchify + torch.cdist + torch.argmin of Codebook.get_patches_bmu
 // (/root/reference/models/Codebook.py:77-99) for fine patches (BASELINE config 2: P=2, D=16, K=4096).
@@ -423,10 +428,14 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                             float q[4];
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                float m8 = __uint_as_float(v[g * 8]);
-#pragma unroll
-                                for (int i = 1; i < 8; ++i) m8 = fminf(m8, __uint_as_float(v[g * 8 + i]));
-                                q[g] = m8;
+                                // balanced tree of 3-input minima (FMNMX3 runs at half rate on the ALU pipe: depth, not
+                                // only count, decides how well two epilogue warps fill it)
+                                const float a = fminf(fminf(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+                                                      __uint_as_float(v[g * 8 + 2]));
+                                const float b = fminf(fminf(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4])),
+                                                      __uint_as_float(v[g * 8 + 5]));
+                                const float c = fminf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+                                q[g] = fminf(fminf(a, b), c);
                             }
                             const float m = fminf(fminf(q[0], q[1]), fminf(q[2], q[3]));
                             if (m < best[r]) {
@@ -435,6 +444,21 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                                 bidx[r] = col0 + c * 32 + sub * CHUNK;
                             }
                         };
+                        if (P.dbg & 6) {
+                            // timing elimination (experiment builds): 2 = loads without the reduction, 4 = no loads
+                            if (P.dbg & 2) {
+                                tmem_ld32_issue(taddr, va); tmem_ld_wait(va);
+                                tmem_ld32_issue(taddr + 32, vb); tmem_ld_wait(vb);
+                                tmem_ld32_issue(taddr + 64, va); tmem_ld_wait(va);
+                                tmem_ld32_issue(taddr + 96, vb); tmem_ld_wait(vb);
+                                if (va[0] == 0x7fc12345u && vb[0] == 0x7fc12345u) best[r] = 0.f;
+                            }
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bars.acc_empty[acc]);
+                            ++j;
+                            continue;
+                        }
                         tmem_ld32_issue(taddr, va);
                         tmem_ld_wait(va);
                         tmem_ld32_issue(taddr + 32, vb);
@@ -597,7 +621,7 @@ size_t tc_s_workspace_bytes(int64_t n_patches, int D, int K) {
 // FP16-split mode of the config-S kernel (default) or the 3xTF32 one: SOM_TC_S_F16=0 / 1, read once per process
 static bool tc_s_f16_mode() {
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("SOM_TC_S_F16"); mode = e ? (atoi(e) != 0) : 0; }
+    if (mode < 0) { const char* e = getenv("SOM_TC_S_F16"); mode = e ? (atoi(e) != 0) : 1; }
     return mode != 0;
 }
 
