@@ -375,8 +375,8 @@ def main():
     # ---- roofline of the dominant kernel (BMU) --------------------------------------------------
     flops = 2.0 * k * d_dim * n_p
     achieved = flops / (ms_step * 1e-3) / 1e12
-    # config-S split mode of the library (csrc/som_bmu_tc_s.cu): FP16 hi/lo by default, TF32 with SOM_TC_S_F16=0
-    f16_split = variant == 2 and os.environ.get("SOM_TC_S_F16", "1") != "0"
+    # config-S split mode of the library (csrc/som_bmu_tc_s.cu): FP16 hi/lo from 65 536 patches on, TF32 below or with SOM_TC_S_F16=0
+    f16_split = variant == 2 and os.environ.get("SOM_TC_S_F16", "1") != "0" and n_p >= 65536
     bf16_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     tc_peak = bf16_peak / 3.0 if f16_split else bf16_peak * 0.5 / 3.0
     traffic, pipe_pct = None, None
@@ -384,8 +384,8 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        traffic = tj.get("bmu_c2_dram_bytes_per_launch")
-        pipe_pct = tj.get("bmu_c2_tensor_pipe_active_pct")
+        traffic = tj.get("bmu_c2_f16_dram_bytes_per_launch" if f16_split else "bmu_c2_dram_bytes_per_launch")
+        pipe_pct = tj.get("bmu_c2_f16_tensor_pipe_active_pct" if f16_split else "bmu_c2_tensor_pipe_active_pct")
     # nominal fp32-faithful roof of this shape: 2048 TF32 MAC/clk/SM x 148 SMs x max clock / 3 products,
     # times the useful fraction of the K' = 3*16 + 8 inner dimension
     nominal = 2048 * 2 * 148 * 1.965e9 / 3.0 * (48.0 / 56.0) / 1e12

@@ -554,7 +554,23 @@ __global__ void __launch_bounds__(1024) cb_scale_kernel(const float* __restrict_
     __shared__ float sh_c[32], sh_n[32];
     float mc = 0.f, mn = 0.f;
     const int64_t total = (int64_t)K * D;
-    for (int64_t i = threadIdx.x; i < total; i += 1024) mc = fmaxf(mc, fabsf(W[i]));
+    if ((reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+        // four 16-byte loads in flight per thread: one CTA is latency-bound otherwise
+        const float4* W4 = reinterpret_cast<const float4*>(W);
+        const int64_t n4 = total >> 2;
+        for (int64_t i = threadIdx.x; i < n4; i += 4096) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                q[u] = (i + u * 1024 < n4) ? __ldg(W4 + i + u * 1024) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                mc = fmaxf(fmaxf(mc, fmaxf(fabsf(q[u].x), fabsf(q[u].y))), fmaxf(fabsf(q[u].z), fabsf(q[u].w)));
+        }
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < total; i += 1024) mc = fmaxf(mc, fabsf(W[i]));
+    } else {
+        for (int64_t i = threadIdx.x; i < total; i += 1024) mc = fmaxf(mc, fabsf(W[i]));
+    }
     for (int i = threadIdx.x; i < K; i += 1024) mn = fmaxf(mn, fabsf(cn[i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -618,11 +634,13 @@ size_t tc_s_workspace_bytes(int64_t n_patches, int D, int K) {
     return align_up(K_pad * 32 * 4, 1024) + align_up(K_pad * 8 * 4, 1024) + 1024;     // + the FP16 mode's scale slot
 }
 
-// FP16-split mode of the config-S kernel (default) or the 3xTF32 one: SOM_TC_S_F16=0 / 1, read once per process
-static bool tc_s_f16_mode() {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("SOM_TC_S_F16"); mode = e ? (atoi(e) != 0) : 1; }
-    return mode != 0;
+// Split mode of the config-S kernel.  Static rule: FP16 from 65 536 patches on (C2: 4.1-4.3 vs 4.8-4.9 ms); below that
+// a launch is tens of microseconds and the extra scale pre-pass (one CTA, a few us) would eat the gain, so small batches
+// keep the 3xTF32 mode.  SOM_TC_S_F16 = 1 / 0 forces FP16 / TF32 for every size (read once per process; tests, A/B).
+static bool tc_s_f16_mode(int64_t n_patches) {
+    static int mode = -2;
+    if (mode == -2) { const char* e = getenv("SOM_TC_S_F16"); mode = e ? (atoi(e) != 0) : -1; }
+    return mode < 0 ? n_patches >= 65536 : mode != 0;
 }
 
 int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
@@ -639,7 +657,7 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
     float* Bp = (float*)ws;
     float* Tp = (float*)((char*)ws + align_up((size_t)K_pad * 32 * 4, 1024));
     float* scale = (float*)((char*)Tp + align_up((size_t)K_pad * 8 * 4, 1024));
-    const bool f16 = tc_s_f16_mode();
+    const bool f16 = tc_s_f16_mode(n);
     if (f16) {
         cb_scale_kernel<<<1, 1024, 0, st>>>(W, cn, K, D, scale);
         int rc = check_launch("cb_scale_kernel");
