@@ -54,7 +54,10 @@ extern "C" {
 /* BMU kernel variants (static rule in som_bmu_pick_variant; no runtime autotuner) */
 #define SOM_BMU_AUTO         0
 #define SOM_BMU_FFMA         1   /* fp32 FFMA register-tiled kernel, any shape                  */
-#define SOM_BMU_TC3X         2   /* tcgen05 kind::tf32, 3xTF32 error-compensated, TMEM argmin   */
+#define SOM_BMU_TC3X         2   /* tcgen05, error-compensated hi/lo split (3 products), TMEM argmin:
+                                  * kind::tf32 3xTF32; for D <= 16 and >= 65 536 patches a kind::f16 FP16
+                                  * split with exact power-of-two scaling (same 11+11-bit operand precision,
+                                  * fp32 accumulation; environment SOM_TC_S_F16=0 keeps 3xTF32 everywhere)  */
 
 SOM_API int         som_version(void);
 SOM_API const char* som_last_error(void);

@@ -1,7 +1,7 @@
 // K1 (tensor-core variant), small patch dimension D <= 16 ("config S"): BMU search as an
 // error-compensated split GEMM on tcgen05 with the argmin fused into the TMEM epilogue.  sm_100a only.
-// Two operand splits share the pipeline: FP16 hi/lo with power-of-two scaling (default: kind::f16, 4 MMAs per
-// 128 x 256 tile, see the note above the kernel) and TF32 hi/lo (SOM_TC_S_F16=0: kind::tf32, 7 MMAs per tile,
+// Two operand splits share the pipeline: FP16 hi/lo with power-of-two scaling (from 65 536 patches on: kind::f16,
+// 4 MMAs per 128 x 256 tile, see the note above the kernel) and TF32 hi/lo (SOM_TC_S_F16=0: kind::tf32, 7 MMAs per tile,
 // described first below).  Measured at C2: 4.1-4.3 ms vs 4.8-4.9 ms per 10 000 128 patches; in the FP16 mode the
 // min-reduction of the epilogue (half-rate FMNMX on the ALU pipe, ~300 cycles per tile) and not the tensor pipe
 // (512 cycles per tile) sets the pace: 850 cycles per tile, 547 with the reduction switched off.
