@@ -257,16 +257,16 @@ def test_reduced_distance_accuracy_of_both_variants(fmaps, p, k, bound):
         assert err <= bound, f"variant {variant}: rd error {err:.2e} > {bound}"
 
 
-@pytest.mark.parametrize("fmaps,p,k", [(64, 2, 4096), (16, 4, 4096), (64, 4, 2100), (32, 8, 2048), (16, 8, 20000),
-                                       (64, 32, 512), (3, 8, 777)])
+@pytest.mark.parametrize("fmaps,p,k", [(64, 2, 4096), (320, 2, 4096), (16, 4, 4096), (64, 4, 2100), (32, 8, 2048),
+                                       (16, 8, 20000), (64, 32, 512), (3, 8, 777)])
 def test_non_finite_patches_take_unit_zero_and_leave_their_neighbours_alone(fmaps, p, k):
     """Non-finite input (a diverged encoder).  The reference's distance row of a patch that holds a NaN is all
     NaN and torch.argmin returns its first position, unit 0 (models/Codebook.py:86-94; the training loop then
     stops on its NaN-loss guard, train_codebook.py:237-238).  Every kernel mode must return 0 for such a patch
     as well, an in-range index for a patch that holds +-inf (the reference's own pick there depends on which
     inf - inf of its sgemm turns into NaN first), and exactly the clean-run index for every other patch, also
-    for the rows that share a 128-row MMA tile with a poisoned one.  Shapes: config S, resident-A, unit split,
-    streamed, streamed with a large codebook, split-K, ragged."""
+    for the rows that share a 128-row MMA tile with a poisoned one.  Shapes: config S in its TF32 and (81 920 patches)
+    FP16-split mode, resident-A, unit split, streamed, streamed with a large codebook, split-K, ragged."""
     pd = (p, p)
     d = 4 * p * p
     x = synthetic_fmaps(fmaps, 23)
