@@ -327,21 +327,27 @@ bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     mbar_wait_warp<true>(&bars.a_empty[r], a_epar, lane);
                     uint8_t* slot = a_slots + (size_t)r * A_BLK_BYTES + row_off;
                     if (F16) {
-                        // power-of-two row scale: max |s_p x| in [64, 128) as long as a_p = s_p / t_c stays an FP16
-                        // normal (2^-14 .. 2^15; beyond that the row moves away from the ideal range binade by binade);
-                        // an all-zero or non-finite row takes the ideal exponent 0
+                        // power-of-two row scale: max |s_p x| in [64, 128) as long as a_p = s_p / t_c is an exact FP16
+                        // power of two (2^-24 .. 2^15); an all-zero or non-finite row takes the ideal exponent 0
                         float m = 0.f;
 #pragma unroll
                         for (int d = 0; d < DMAX; ++d) m = fmaxf(m, fabsf(xv[r][d]));
                         const int eb = (int)((__float_as_uint(m) >> 23) & 0xffu);
                         int ep = 133 - eb;
                         if (!(m > 0.f) || eb == 0xff) ep = 0;
-                        int ka = ep - tc_exp;
-                        ka = ka > 15 ? 15 : (ka < -14 ? -14 : ka);
-                        int es = ka + tc_exp;
+                        int ka = ep - tc_exp, es;
+                        float ap;
+                        if (ka < -24) {
+                            // |x| beyond ~2^24 |c|: ||c||^2 is below fp32 resolution of rd; keep the row in range instead
+                            es = ep;
+                            ap = 0.f;
+                        } else {
+                            ka = ka > 15 ? 15 : ka;                 // 2^-24 .. 2^15: exact in FP16 (subnormal below 2^-14)
+                            es = ka + tc_exp;
+                            ap = __uint_as_float((uint32_t)(127 + ka) << 23);
+                        }
                         es = es > 120 ? 120 : (es < -120 ? -120 : es);
                         const float sp = __uint_as_float((uint32_t)(127 + es) << 23);
-                        const float ap = __uint_as_float((uint32_t)(127 + ka) << 23);
                         float hi[DMAX], lo[DMAX];
 #pragma unroll
                         for (int d = 0; d < DMAX; ++d) {
