@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- SOM-codebook hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU)
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU, torchrun for N > 1)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
 
-Workload at every N (weak scaling, patches shard across ranks, no data-path collective):
-BASELINE.json configs[1] -- fine-patch tokenisation, P=2 (D=16), 4096-unit codebook, 39 063
-synthetic 4x32x32 latent fmaps = 10 000 128 patches per GPU per step, BMU only.  One step = one pass
-of Codebook.get_patches_bmu over that batch.  `value` has the inputs resident in HBM; `e2e` runs
-the same batch from pinned HOST memory through somcb.HostTokenizer (H2D + BMU + D2H of int64
-indices inside the timed region).  Prints ONE JSON line on rank 0.
+Headline workload at every N (BASELINE.json `metric` = patches/sec BMU+update; configs[3], C4): ONE SOM training step
+of /root/reference/train_codebook.py:225-249 -- BMU search + neighbourhood-weighted update + Adam -- at P=4 (D=64),
+K=16 384 units, on a FIXED GLOBAL batch of 16 384 synthetic 4x32x32 feature maps = 1 048 576 patches per step, split
+over the N ranks (patch-sharded data parallel, STRONG scaling).  Every step of every N > 1 run contains the NCCL
+all-reduce of the packed per-unit accumulators (4 MB) inside the timed region; the whole step is a CUDA graph.
+`value` has the batches resident in HBM; `e2e` feeds the same step from pinned HOST memory through somcb.HostTrainer
+(H2D copy of every batch and D2H read of every loss inside the timed region).  `extra` carries BASELINE configs[1]
+(C2, BMU-only tokenisation, with its own roofline and e2e), configs[4] (C5, unit-sharded search + histogram over the
+N ranks), C1 / C3 step times, and -- for N > 1 -- in-run parity checks (replicas identical, DP == 1-GPU trainer,
+sharded search == unsharded search).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -31,11 +35,17 @@ if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
 
 import torch  # noqa: E402
 
-METRIC = "patches/sec BMU (fine-patch tokenisation P=2 D=16 K=4096, 10M patches/step/GPU)"
+METRIC = "patches/sec BMU+update (SOM training step P=4 D=64 K=16384, 1 048 576 patches per step over all GPUs)"
 UNIT = "patches/s"
+C4 = dict(n_fmaps=16384, patch=(4, 4), K=16384, C=4, H=32, W=32, D=64, seq=64, lr=1e-4, neighbourhood_step=200)
 C2 = dict(n_fmaps=39063, patch=(2, 2), K=4096, C=4, H=32, W=32)
+WORKLOAD = ("BASELINE configs[3] (C4): SOM training step (BMU + neighbourhood update + Adam, "
+            "train_codebook.py:225-249), P=4 (D=64), K=16384 trained-like codebook, range 8192, fixed global batch of "
+            "16 384 synthetic 4x32x32 fmaps = 1 048 576 patches per step, patch-sharded over the GPUs")
+CONFIG = {"workload": WORKLOAD, "global_patches_per_step": C4["n_fmaps"] * C4["seq"], "D": 64, "K": 16384,
+          "parallelism": "patch-sharded data parallel, one all-reduce of the packed accumulators per step"}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # derived: 74.4 at max clock
+L2_BYTES = 126 << 20
 
 
 def _peaks():
@@ -51,7 +61,7 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock / throttle reasons through NVML (~1 kHz) while the timed region runs."""
 
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
@@ -88,7 +98,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def __enter__(self):
         if self.nv is not None:
@@ -106,14 +116,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
         s = sorted(self.samples)
         reasons = sorted(r for r in self.reasons if r not in ("GpuIdle", "None", "ApplicationsClocksSetting"))
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+        return {"sm_mhz": s[len(s) // 2], "sm_min_mhz": s[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
                 "samples": len(s)}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic inputs: tanh(randn) fmaps, trained-like codebooks -- restated here so that the measured
+# arm imports nothing from oracle/
+# ---------------------------------------------------------------------------------------------------------------
 def _trained_like_codebook(k, patch, seed=7):
-    """Seeded synthetic codebook for OUR arm: K distinct data patches drawn from an independent pool of
-    tanh(randn) fmaps.  Same recipe as the oracle's helper, restated here so that the measured
-    arm imports nothing from oracle/."""
     import somcb
     p_h, p_w = patch
     seq = (32 // p_h) * (32 // p_w)
@@ -126,163 +137,422 @@ def _trained_like_codebook(k, patch, seed=7):
     return pool[pick].clone().contiguous()
 
 
-def _c2_inputs(dev, seed):
+def _fmaps(n, seed, dev):
     g = torch.Generator(device=dev).manual_seed(seed)
-    x = torch.empty(C2["n_fmaps"], C2["C"], C2["H"], C2["W"], device=dev)
-    for lo in range(0, C2["n_fmaps"], 8192):
-        hi = min(C2["n_fmaps"], lo + 8192)
-        x[lo:hi] = torch.tanh(torch.randn(hi - lo, C2["C"], C2["H"], C2["W"], generator=g, device=dev))
+    x = torch.empty(n, 4, 32, 32, device=dev)
+    for lo in range(0, n, 8192):
+        hi = min(n, lo + 8192)
+        x[lo:hi] = torch.tanh(torch.randn(hi - lo, 4, 32, 32, generator=g, device=dev))
     return x
 
 
-def _c2_codebook(dev=None):
+def _codebook(k, patch, dev, rng=None, seed=7):
     import somcb
-    w = _trained_like_codebook(C2["K"], C2["patch"], 7)
-    cb = somcb.Codebook(patch_dim=C2["patch"], image_dim=(C2["H"], C2["W"]), image_channel=C2["C"],
-                        num_embeddings=C2["K"], init_neighbour_range=C2["K"] // 2)
+    cb = somcb.Codebook(patch_dim=patch, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                        init_neighbour_range=k // 2 if rng is None else rng)
     with torch.no_grad():
-        cb.codebook.weight.copy_(w)
-    return (cb.to(dev) if dev is not None else cb), w
+        cb.codebook.weight.copy_(_trained_like_codebook(k, patch, seed))
+    return cb.to(dev) if dev is not None else cb
 
 
-def _cpu_reference_bmu(steps, warmup, sample_fmaps=256, min_seconds=0.0):
-    """The reference's CPU path for this workload (oracle port, all host threads): patches/s."""
-    from oracle.step_oracle import make_oracle_codebook, synthetic_fmaps, trained_like_codebook
+def _timed(fn, reps, warm=2):
+    """Average device time of fn (ms), CUDA events on the current stream."""
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _max_over_ranks(ms, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU implementation of the step (oracle port), bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_reference_step(steps, warmup, sample_fmaps=128, min_seconds=0.0):
+    """train_codebook.py:225-249 on the host cores at the C4 shape, 8192 patches per step (the reference's dense N x K
+    temporaries need 16*N*K bytes): patches/s."""
+    from oracle.step_oracle import (make_oracle_codebook, make_reference_optimizer, reference_step,
+                                    synthetic_fmaps, trained_like_codebook)
     torch.set_num_threads(os.cpu_count() or 1)
-    w = trained_like_codebook(C2["K"], C2["patch"], 7)
-    cb = make_oracle_codebook(w, C2["patch"], (C2["H"], C2["W"]), C2["C"], C2["K"] // 2)
+    w = trained_like_codebook(C4["K"], C4["patch"], 7)
+    cb = make_oracle_codebook(w, C4["patch"], (32, 32), 4, C4["K"] // 2)
+    opt = make_reference_optimizer(cb, C4["lr"])
     x = synthetic_fmaps(sample_fmaps, 123)
-    n_p = sample_fmaps * 256
-    with torch.no_grad():
-        for _ in range(warmup):
-            cb.get_patches_bmu(x, reshape=True)
-        t0 = time.perf_counter()
-        done = 0
-        while done < steps or (time.perf_counter() - t0) < min_seconds:
-            cb.get_patches_bmu(x, reshape=True)
-            done += 1
-        dt = time.perf_counter() - t0
+    n_p = sample_fmaps * C4["seq"]
+    for _ in range(warmup):
+        reference_step(cb, opt, x)
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps or (time.perf_counter() - t0) < min_seconds:
+        reference_step(cb, opt, x)
+        done += 1
+    dt = time.perf_counter() - t0
     return {"value": n_p * done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{done} calls x {n_p} patches (of the 10 000 128-patch step), oracle restatement of "
-                      f"models/Codebook.py:77-99 on torch {torch.__version__} CPU, {dt:.1f} s"}, dt / done
+            "sample": f"{done} steps x {n_p} patches (a {sample_fmaps}-fmap sample of the 16 384-fmap step; the "
+                      f"reference's dense N x K temporaries do not fit more), oracle restatement of "
+                      f"train_codebook.py:225-249 + models/Codebook.py on torch {torch.__version__} CPU, {dt:.1f} s"}, \
+        dt / done
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, ms = _cpu_reference_bmu(args.steps, args.warmup)
+    steps = max(1, min(args.steps, 40))
+    base, s_per_step = _cpu_reference_step(steps, min(args.warmup, 2))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "BASELINE configs[1] (C2): P=2 D=16 K=4096 BMU-only, "
-                                            "each step a 65 536-patch sample of the 10 000 128-patch batch"},
-            "cpu_baseline": base,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": CONFIG, "cpu_baseline": base,
+            "steps_run": steps,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def _extra_training(dev, world, rank, group):
-    """BMU + update step (BASELINE config 4 shape: P=4 D=64 K=16384, 2^20 patches per GPU per step)."""
+# ---------------------------------------------------------------------------------------------------------------
+# headline: the C4 step, strong-scaled
+# ---------------------------------------------------------------------------------------------------------------
+def _make_trainer(cb, world, graph=True):
     import somcb
-    k, pd, n_f = 16384, (4, 4), 16384
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    x = torch.tanh(torch.randn(n_f, 4, 32, 32, generator=g, device=dev))
-    cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
-                        init_neighbour_range=k // 2)
-    with torch.no_grad():
-        cb.codebook.weight.copy_(_trained_like_codebook(k, pd, 7))
-    cb = cb.to(dev)
-    tr = somcb.DataParallelSom(cb, lr=1e-4, neighbourhood_step=200) if world > 1 else \
-        somcb.SomTrainer(cb, lr=1e-4, neighbourhood_step=200)
-    for _ in range(3):
-        tr.step(x)
-    steps = 5
+    kw = dict(lr=C4["lr"], neighbourhood_step=C4["neighbourhood_step"], use_cuda_graph="alias" if graph else False)
+    return somcb.DataParallelSom(cb, **kw) if world > 1 else somcb.SomTrainer(cb, **kw)
+
+
+def run_headline(args, dev, world, rank, peaks):
+    import somcb
+    import torch.distributed as dist
+    from somcb import ops
+    lib = somcb._lib.load()
+    lo, hi = somcb.shard_bounds(C4["n_fmaps"], world, rank)
+    share = hi - lo
+    share_bytes = share * 4 * 32 * 32 * 4
+    n_rot = max(2, -(-(256 << 20) // share_bytes))           # rotate through >= 256 MB of distinct batches (> L2)
+    n_rot = min(n_rot, 8)
+    # global batch b = fmaps of seed 5000 + b (generated per rank for its own contiguous share: seeds differ per rank)
+    xs = [_fmaps(share, 5000 + 131 * b + rank, dev) for b in range(n_rot)]
+    cb = _codebook(C4["K"], C4["patch"], dev)
+    tr = _make_trainer(cb, world)
+    if world > 1:
+        tr.broadcast_weights(0)
+    # set-up (untimed, before the warm-up): one eager step (kernel attributes, NCCL communicator), then one graph
+    # capture per rotation buffer
+    l0 = lib.som_launch_count()
+    tr.step(xs[0])
+    launches_per_step = int(lib.som_launch_count() - l0)
+    for b in range(n_rot):
+        tr.step(xs[b])
+    torch.cuda.synchronize()
+    it = 0
+    for _ in range(args.warmup):
+        tr.step(xs[it % n_rot])
+        it += 1
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
-        torch.distributed.barrier()
+        dist.barrier()
     torch.cuda.synchronize()
-    e0.record()
-    for _ in range(steps):
-        loss = tr.step(x)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-    ms = float(ms) / steps
-    return {"workload": "C4 shape: SOM step (BMU + accumulate + 2 filters + Adam), P=4 D=64 K=16384, "
-                        "1 048 576 patches/GPU/step" + (", all-reduce of Rbar per step" if world > 1 else ""),
-            "patches_per_s": world * n_f * 64 / (ms * 1e-3), "ms_per_step": ms, "loss": float(loss)}
-
-
-def _extra_configs(dev):
-    """Single-GPU timings of the other BASELINE shapes (device time, CUDA events): C1 step with CUDA-graph
-    replay, C3 BMU + full step, C5 one GPU's shard BMU.  Reported beside the headline, not part of it."""
-    import somcb
-    from somcb import ops
-
-    def data(n, seed):
-        g = torch.Generator(device=dev).manual_seed(seed)
-        x = torch.empty(n, 4, 32, 32, device=dev)
-        for lo in range(0, n, 8192):
-            hi = min(n, lo + 8192)
-            x[lo:hi] = torch.tanh(torch.randn(hi - lo, 4, 32, 32, generator=g, device=dev))
-        return x
-
-    def timed(fn, reps, warm=3):
-        for _ in range(warm):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
+    with ClockSampler(dev.index) as clk:
         e0.record()
-        for _ in range(reps):
-            fn()
+        for _ in range(args.steps):
+            loss = tr.step(xs[it % n_rot])
+            it += 1
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
+    if world > 1:
+        dist.barrier()
+    ms_step = _max_over_ranks(e0.elapsed_time(e1), dev, world) / args.steps
+    n_global = C4["n_fmaps"] * C4["seq"]
+    value = n_global / (ms_step * 1e-3)
+    loss = float(loss)
+    assert loss == loss and 0.0 < loss < 10.0, f"implausible loss {loss}"
 
-    def codebook(k, pd, rng):
-        d = 4 * pd[0] * pd[1]
-        pool = data(max(8, (k * d) // 4096 + 1), 7)
-        w = somcb.patchify(pool, pd).reshape(-1, d)[:k].contiguous()
-        cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
-                            init_neighbour_range=rng).to(dev)
-        with torch.no_grad():
-            cb.codebook.weight.copy_(w)
-        return cb
+    # ---- end to end: pinned host batches -> H2D -> step -> loss D2H, every step ----------------------------------
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    cpus_before = os.sched_getaffinity(0)
+    numa_node = somcb.bind_host_to_gpu_node(dev)
+    hosts = [torch.empty(share, 4, 32, 32, pin_memory=True) for _ in range(2)]
+    for b in range(2):
+        hosts[b].copy_(xs[b])
+    ht = somcb.HostTrainer(tr, depth=2)
+    pend = None
+    for b in range(4):                                       # graph capture on the two staging buffers + warm-up
+        pend = ht.step(hosts[b % 2])
+    pend.item()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    prev = None
+    for b in range(e2e_steps):
+        cur = ht.step(hosts[b % 2])
+        if prev is not None:
+            prev.item()                                      # the host reads every step's loss (one step behind)
+        prev = cur
+    last_loss = prev.item()
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_ms = _max_over_ranks(f0.elapsed_time(f1), dev, world) / e2e_steps
+    # copy floor: the same H2D bytes alone, all ranks at once
+    dst = torch.empty_like(xs[0])
 
+    def h2d():
+        dst.copy_(hosts[0], non_blocking=True)
+    if world > 1:
+        dist.barrier()
+    floor_ms = _max_over_ranks(_timed(h2d, 5, warm=1), dev, world)
+    os.sched_setaffinity(0, cpus_before)
+    del hosts, ht, dst
+    e2e = {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "h2d_bytes_per_step": share * 4 * 32 * 32 * 4, "d2h_bytes_per_step": 8,
+           "bytes_note": "per rank: its share of the step's fmaps in, the loss scalar out",
+           "copy_floor_ms": floor_ms, "frac_of_copy_floor": floor_ms / e2e_ms,
+           "api": "somcb.HostTrainer(trainer).step(pinned fmaps) -> PendingLoss.item()", "host_numa_node": numa_node,
+           "last_loss": last_loss}
+
+    # ---- per-kernel breakdown of one rank's step (each op timed alone, CUDA events) ------------------------------
+    x = xs[0]
+    geom = ops.geometry(x.shape, C4["patch"])
+    w = cb.codebook.weight.data
+    k, d, rng = C4["K"], C4["D"], cb.neighbourhood_range
+    cn = ops.prepare_codebook(w)
+    wt = ops.neighbourhood_filter(w, rng)
+    bmu = ops.bmu(x, geom, w, cn)
+    packed = torch.empty(k * d + 4, dtype=torch.float32, device=dev)
+    ops.accumulate_packed(x, geom, bmu, wt, k, packed=packed)
+    wc, mc, vc = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    tdev = torch.ones(1, dtype=torch.int64, device=dev)
+    grad = ops.neighbourhood_filter(packed[:k * d].view(k, d), rng)
+    reps = 10
+    parts = {"filter_W": _timed(lambda: ops.neighbourhood_filter(w, rng), reps),
+             "norms": _timed(lambda: ops.prepare_codebook(w), reps),
+             "bmu": _timed(lambda: ops.bmu(x, geom, w, cn), reps),
+             "accumulate": _timed(lambda: ops.accumulate_packed(x, geom, bmu, wt, k, packed=packed), reps),
+             "filter_Rbar": _timed(lambda: ops.neighbourhood_filter(packed[:k * d].view(k, d), rng), reps),
+             "adam": _timed(lambda: ops.adam_step_dp(wc, mc, vc, grad, d, 1e-4, tdev, packed[k * d:]), reps)}
+    if world > 1:
+        scratch = packed.clone()
+        dist.barrier()
+        parts["all_reduce"] = _timed(lambda: dist.all_reduce(scratch), reps)
+    parts = {kk: _max_over_ranks(v, dev, world) for kk, v in parts.items()}
+    ksum = sum(parts.values())
+    breakdown = {kk: {"ms": v, "pct_of_step": 100.0 * v / ms_step} for kk, v in parts.items()}
+    breakdown["sum_of_parts_ms"] = ksum
+    breakdown["graph_step_ms"] = ms_step
+    breakdown["note"] = ("each op timed alone (eager, its own pre-pass launches included) on one rank's share, max "
+                         "over ranks; the step itself is one CUDA-graph replay")
+
+    # ---- roofline of the dominant kernel (BMU) --------------------------------------------------------------------
+    n_local = share * C4["seq"]
+    flops = 2.0 * k * d * n_local
+    achieved = flops / (parts["bmu"] * 1e-3) / 1e12
+    mode = os.environ.get("SOM_BMU_VARIANT_NOTE", "")
+    split = lib.som_bmu_split_mode(n_local, d, k) if hasattr(lib, "som_bmu_split_mode") else 0
+    f16 = split == 1
+    peak_burst = peaks["bf16_tflops"] / (3.0 if f16 else 6.0)
+    peak_sust = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / (3.0 if f16 else 6.0)
+    traffic, pipe_pct, src = None, None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        key = "bmu_c4_f16" if f16 else "bmu_c4"
+        traffic = tj.get(key + "_dram_bytes_per_launch")
+        pipe_pct = tj.get(key + "_tensor_pipe_active_pct")
+        src = tj.get(key + "_source")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
+                "frac": achieved / peak_burst, "traffic": traffic,
+                "traffic_source": (f"constant from {src} (one ncu --set full capture at N=1), not measured in this run"
+                                   if traffic is not None else None),
+                "kernel": ("bmu_tc_l16 (tcgen05 kind::f16, FP16 hi/lo split x3 products, fp32 accumulate in TMEM)" if f16
+                           else "bmu_tc_l (tcgen05 kind::tf32 x3)"),
+                "peak_basis": (f"{peaks['_source']}: BURST cuBLAS bf16 {peaks['bf16_tflops']} TFLOP/s / 3 (three 16-bit "
+                               "products per fp32-faithful product)" if f16 else
+                               f"{peaks['_source']}: BURST cuBLAS bf16 / 2 (tf32) / 3 (3xTF32)"),
+                "frac_of_sustained_basis": achieved / peak_sust,
+                "launch_ms": parts["bmu"], "patches_per_launch": n_local,
+                "algorithmic_flops_per_patch": 2 * k * d, "algorithmic_bytes_per_patch": 4 * d + 8,
+                "hbm_frac": (4 * d + 8) * n_local / (parts["bmu"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "tensor_pipe_active_pct_ncu": pipe_pct, "note": mode or None}
+    head = {"value": value, "ms_per_step": ms_step, "loss": loss, "clocks": clk.summary(), "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "breakdown": breakdown,
+            "details": {"fmaps_per_rank": share, "patches_per_rank": n_local, "rotation_buffers": n_rot,
+                        "launches_per_step": launches_per_step,
+                        "launch_note": "kernels of libsomcb per step, replayed from one CUDA graph per rotation buffer "
+                                       "(+ the NCCL all-reduce kernel for N > 1)",
+                        "l2": f"each rank rotates through {n_rot} distinct resident batches "
+                              f"({n_rot * share_bytes >> 20} MB > the 126 MB L2), so no step re-reads a batch that is "
+                              "still L2 resident",
+                        "allreduce_bytes_per_step": (k * d + 4) * 4 if world > 1 else 0}}
+    return head, tr, cb, xs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# in-run parity checks at N > 1
+# ---------------------------------------------------------------------------------------------------------------
+def run_checks(tr, cb, dev, world, rank):
+    import somcb
+    import torch.distributed as dist
+    from somcb import ops
     out = {}
-    x1, cb1 = data(8, 123), codebook(1024, (4, 4), 512)
+    # (1) replicas bit-identical after the timed steps
+    w = cb.codebook.weight.data
+    ref = w.clone()
+    dist.broadcast(ref, src=0)
+    same = torch.tensor([1 if torch.equal(ref, w) else 0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    out["replicas_bit_identical_after_timed_steps"] = bool(int(same))
+    # (2) DP over the ranks == a 1-GPU trainer on the whole 65 536-patch batch (2 steps, same start)
+    x = _fmaps(1024, 777, dev)                               # same seed on every rank: the same global batch
+    cb_dp, cb_one = _codebook(C4["K"], C4["patch"], dev), _codebook(C4["K"], C4["patch"], dev)
+    dp = somcb.DataParallelSom(cb_dp, lr=1e-4, neighbourhood_step=200)
+    one = somcb.SomTrainer(cb_one, lr=1e-4, neighbourhood_step=200)
+    rel_l = 0.0
+    for _ in range(2):
+        l_dp = dp.step(somcb.split_batch(x, world, rank).contiguous())
+        l_one = one.step(x)
+        rel_l = max(rel_l, abs(float(l_dp) - float(l_one)) / abs(float(l_one)))
+    w_dp, w_one = cb_dp.codebook.weight.data.double(), cb_one.codebook.weight.data.double()
+    rel_w = torch.tensor([float((w_dp - w_one).norm() / w_one.norm()), rel_l], device=dev, dtype=torch.float64)
+    dist.all_reduce(rel_w, op=dist.ReduceOp.MAX)
+    out["dp_vs_single_gpu_2_steps_65536_patches"] = {"weights_rel_fro": float(rel_w[0]), "loss_rel": float(rel_w[1]),
+                                                     "ok": bool(rel_w[0] <= 1e-6 and rel_w[1] <= 1e-6)}
+    # (3) unit-sharded search over the ranks == the unsharded search (same codebook, 65 536 patches)
+    wfull = cb_one.codebook.weight.data
+    geom = ops.geometry(x.shape, C4["patch"])
+    full = ops.bmu(x, geom, wfull)
+    lo, hi = somcb.shard_bounds(C4["K"], world, rank)
+    got = somcb.sharded_bmu(x, geom, wfull[lo:hi].contiguous(), lo)
+    diff = torch.nonzero(got != full).flatten()
+    ok = True
+    if diff.numel():
+        flat = somcb.patchify(x, C4["patch"]).reshape(-1, 64)[diff].double()
+        da = (flat - wfull[got[diff]].double()).norm(dim=1)
+        db = (flat - wfull[full[diff]].double()).norm(dim=1)
+        ok = bool(((da - db).abs() <= 1e-6 * db).all())
+    flag = torch.tensor([1 if ok else 0, int(diff.numel())], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["sharded_bmu_vs_unsharded_65536_patches"] = {"index_differences": int(diff.numel()),
+                                                    "all_within_1e-6_fp64_distance": bool(int(flag[0]))}
+    out["all_ok"] = bool(out["replicas_bit_identical_after_timed_steps"] and
+                         out["dp_vs_single_gpu_2_steps_65536_patches"]["ok"] and int(flag[0]))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# extras: C2 (BMU-only tokenisation), C5 (unit-sharded search + histogram), C1 / C3
+# ---------------------------------------------------------------------------------------------------------------
+def extra_c2(dev, peaks, steps=10):
+    import somcb
+    lib = somcb._lib.load()
+    cb = _codebook(C2["K"], C2["patch"], dev)
+    cb.eval()
+    x = _fmaps(C2["n_fmaps"], 123, dev)
+    n_p = C2["n_fmaps"] * 256
+    with torch.no_grad():
+        ms = _timed(lambda: cb.get_patches_bmu(x, reshape=True), steps, warm=3)
+        idx = cb.get_patches_bmu(x, reshape=True)
+    counts = somcb.ops.histogram(idx.reshape(-1), C2["K"])
+    assert int(counts.sum()) == n_p
+    host = torch.empty(C2["n_fmaps"], 4, 32, 32, pin_memory=True)
+    host.copy_(x)
+    out_host = torch.empty(C2["n_fmaps"], 256, dtype=torch.int64, pin_memory=True)
+    tok = somcb.HostTokenizer(cb, chunk_fmaps=4096, depth=3)
+    e2e_ms = _timed(lambda: tok.tokenize(host, out_host), 5, warm=2)
+    assert torch.equal(out_host, idx.cpu()), "e2e indices differ from the resident-input run"
+    dst = torch.empty_like(x)
+    floor_ms = _timed(lambda: dst.copy_(host, non_blocking=True), 3, warm=1)
+    flops = 2.0 * C2["K"] * 16 * n_p
+    achieved = flops / (ms * 1e-3) / 1e12
+    f16 = (lib.som_bmu_split_mode(n_p, 16, C2["K"]) == 1) if hasattr(lib, "som_bmu_split_mode") else True
+    peak = peaks["bf16_tflops"] / (3.0 if f16 else 6.0)
+    return {"workload": "BASELINE configs[1] (C2): 39 063 fmaps, P=2 (D=16), K=4096, 10 000 128 patches, BMU only",
+            "value": n_p / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "dtype": "f32 (fp16 hi/lo x3 screen, fp32 accumulate, exact fp32 resolve of the winning chunk)",
+            "e2e": {"value": n_p / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "h2d_bytes_per_step": host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 8, "copy_floor_ms": floor_ms,
+                    "frac_of_copy_floor": floor_ms / e2e_ms,
+                    "api": "somcb.HostTokenizer.tokenize(pinned fmaps) -> pinned int64 indices (synchronous)"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak,
+                         "peak_basis": f"{peaks['_source']}: BURST cuBLAS bf16 / 3 (three 16-bit products)",
+                         "kernel": "bmu_tc_s<F16> (tcgen05 kind::f16)"}}
+
+
+def extra_c5(dev, world, rank):
+    """configs[4]: D=256, K=262 144 units sharded over the ranks (K/N per GPU), 1 048 576 replicated patches (a
+    131 072-patch sample when one GPU holds all units), all-gather + merge + sharded histogram."""
+    import somcb
+    import torch.distributed as dist
+    from somcb import ops
+    from somcb.distributed import sharded_bmu, sharded_histogram
+    k_total = 262144
+    lo, hi = somcb.shard_bounds(k_total, world, rank)
+    n_f = 65536 if world >= 4 else 8192 * world
+    x = _fmaps(n_f, 123, dev)
+    gw = torch.Generator(device=dev).manual_seed(500 + rank)
+    w_shard = torch.tanh(torch.randn(hi - lo, 256, generator=gw, device=dev))
+    geom = ops.geometry(x.shape, (8, 8))
+    cn = ops.prepare_codebook(w_shard)
+    state = {}
+
+    def search():
+        idx = sharded_bmu(x, geom, w_shard, lo, c_norm2=cn)
+        state["counts"] = sharded_histogram(idx, lo, hi)
+
+    search()
+    if world > 1:
+        dist.barrier()
+    ms = _max_over_ranks(_timed(search, 2, warm=0), dev, world)
+    n_p = ops.n_patches_of(geom)
+    tot = state["counts"].sum().to(torch.int64)
+    if world > 1:
+        dist.all_reduce(tot)
+    assert int(tot) == n_p, f"sharded histogram sums to {int(tot)}, expected {n_p}"
+    return {"workload": f"BASELINE configs[4] (C5): D=256, K=262 144 units in {world} shard(s) of {hi - lo}, "
+                        f"{n_p} patches, candidates all-gathered and merged, sharded hit histogram",
+            "ms": ms, "patches_per_s": n_p / (ms * 1e-3), "unit_patch_pairs_per_s": n_p * k_total / (ms * 1e-3),
+            "fp32_faithful_tflops_all_gpus": 2.0 * 256 * k_total * n_p / (ms * 1e-3) / 1e12}
+
+
+def extra_small_configs(dev):
+    import somcb
+    from somcb import ops
+    out = {}
+    x1, cb1 = _fmaps(8, 123, dev), _codebook(1024, (4, 4), dev)
     tr1 = somcb.SomTrainer(cb1, lr=1e-4, neighbourhood_step=10 ** 9, use_cuda_graph="alias")
-    out["C1_step_cuda_graph_us"] = 1e3 * timed(lambda: tr1.step(x1), 100, warm=5)
-    x3, cb3 = data(4096, 123), codebook(512, (32, 32), 256)
+    out["C1_step_cuda_graph_us"] = 1e3 * _timed(lambda: tr1.step(x1), 100, warm=5)
+    x3, cb3 = _fmaps(4096, 123, dev), _codebook(512, (32, 32), dev)
     w3 = cb3.codebook.weight.data
     g3 = ops.geometry(x3.shape, (32, 32))
-    out["C3_bmu_ms"] = timed(lambda: ops.bmu(x3, g3, w3, ops.prepare_codebook(w3)), 20)
+    cn3 = ops.prepare_codebook(w3)
+    out["C3_bmu_ms"] = _timed(lambda: ops.bmu(x3, g3, w3, cn3), 20)
     tr3 = somcb.SomTrainer(cb3, lr=1e-4, neighbourhood_step=10 ** 9, use_cuda_graph="alias")
-    out["C3_step_ms"] = timed(lambda: tr3.step(x3), 20)
-    del x3, tr3, cb3
-    x5, cb5 = data(65536, 123), codebook(32768, (8, 8), 16384)
-    w5 = cb5.codebook.weight.data
-    g5 = ops.geometry(x5.shape, (8, 8))
-    cn5 = ops.prepare_codebook(w5)
-    out["C5_shard_bmu_ms"] = timed(lambda: ops.bmu(x5, g5, w5, cn5), 3, warm=1)
-    out["shapes"] = ("C1: 512 patches D=64 K=1024; C3: 4096 patches D=4096 K=512; "
-                     "C5: 1 048 576 patches D=256, 32 768 of 262 144 units")
+    out["C3_step_ms"] = _timed(lambda: tr3.step(x3), 20)
+    out["shapes"] = "C1: 512 patches D=64 K=1024 (BASELINE configs[0]); C3: 4096 patches D=4096 K=512 (configs[2])"
     return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=96)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 3xTF32")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 10)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 20)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -292,7 +562,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (our arm) needs a CUDA device: somcb has no CPU fallback")
-    import somcb
+    import somcb  # noqa: F401
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -303,153 +573,46 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = somcb._lib.load()
     peaks = _peaks()
 
-    cb, w_cpu = _c2_codebook(dev)
-    cb.bmu_variant = args.variant
-    cb.eval()
-    x = _c2_inputs(dev, 123 + rank)
-    n_p = C2["n_fmaps"] * 256
-    d_dim, k = 16, C2["K"]
-    variant = args.variant or lib.som_bmu_pick_variant(n_p, d_dim, k)
+    head, tr, cb, xs = run_headline(args, dev, world, rank, peaks)
 
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            idx = cb.get_patches_bmu(x, reshape=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        l0 = lib.som_launch_count()
-        with ClockSampler(local) as clk:
-            e0.record()
-            for _ in range(args.steps):
-                idx = cb.get_patches_bmu(x, reshape=True)
-            e1.record()
-            torch.cuda.synchronize()
-        launches = lib.som_launch_count() - l0
-        if world > 1:
-            dist.barrier()
-    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_t) / args.steps
-    value = world * n_p / (ms_step * 1e-3)
-
-    # sanity inside the bench: indices in range and the histogram adds up
-    counts = somcb.ops.histogram(idx.reshape(-1), k)
-    assert int(counts.sum()) == n_p
-
-    # ---- end to end from pinned host memory through the public host API ----------------------
-    e2e_steps = args.e2e_steps or min(args.steps, 10)
-    # one process per GPU: stage out of the GPU's own NUMA node (no-op when the topology is not exposed)
-    cpus_before = os.sched_getaffinity(0)
-    numa_node = somcb.bind_host_to_gpu_node(dev)
-    host = torch.empty(C2["n_fmaps"], C2["C"], C2["H"], C2["W"], pin_memory=True)
-    host.copy_(x)
-    out_host = torch.empty(C2["n_fmaps"], 256, dtype=torch.int64, pin_memory=True)
-    tok = somcb.HostTokenizer(cb, chunk_fmaps=4096, depth=3)
-    for _ in range(2):
-        tok.tokenize(host, out_host)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(e2e_steps):
-        tok.tokenize(host, out_host)
-    f1.record()
-    torch.cuda.synchronize()
-    assert torch.equal(out_host, idx.cpu()), "e2e indices differ from the resident-input run"
-    os.sched_setaffinity(0, cpus_before)            # the CPU baseline below uses every host core again
-    e2e_t = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_t) / e2e_steps
-    e2e = {"value": world * n_p / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 8,
-           "api": "somcb.HostTokenizer.tokenize(pinned fmaps) -> pinned int64 indices",
-           "host_numa_node": numa_node}
-
-    # ---- roofline of the dominant kernel (BMU) --------------------------------------------------
-    flops = 2.0 * k * d_dim * n_p
-    achieved = flops / (ms_step * 1e-3) / 1e12
-    # config-S split mode of the library (csrc/som_bmu_tc_s.cu): FP16 hi/lo from 65 536 patches on, TF32 below or with SOM_TC_S_F16=0
-    f16_split = variant == 2 and os.environ.get("SOM_TC_S_F16", "1") != "0" and n_p >= 65536
-    bf16_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    tc_peak = bf16_peak / 3.0 if f16_split else bf16_peak * 0.5 / 3.0
-    traffic, pipe_pct = None, None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = tj.get("bmu_c2_f16_dram_bytes_per_launch" if f16_split else "bmu_c2_dram_bytes_per_launch")
-        pipe_pct = tj.get("bmu_c2_f16_tensor_pipe_active_pct" if f16_split else "bmu_c2_tensor_pipe_active_pct")
-    # nominal fp32-faithful roof of this shape: 2048 TF32 MAC/clk/SM x 148 SMs x max clock / 3 products,
-    # times the useful fraction of the K' = 3*16 + 8 inner dimension
-    nominal = 2048 * 2 * 148 * 1.965e9 / 3.0 * (48.0 / 56.0) / 1e12
-    # the tensor pipe's own sustained TF32 rate on this pool (tools/mma_rate.cu, power-capped clock), / 3 products
-    pipe_peak = None
-    ppath = os.path.join(ROOT, "profiles", "measured_pipe_peaks.json")
-    if os.path.exists(ppath):
-        with open(ppath) as f:
-            pipe_peak = json.load(f).get("tf32_3x_fp32_faithful_tflops_sustained")
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                "frac": achieved / tc_peak, "traffic": traffic,
-                "kernel": ("bmu_tc_s (tcgen05 kind::f16 x3, FP16 hi/lo split)" if f16_split else
-                           "bmu_tc3x (tcgen05 kind::tf32 x3)") if variant == 2 else "bmu_ffma (fp32 FFMA)",
-                "peak_basis": (f"{peaks['_source']}: sustained bf16 x 1/3 (three 16-bit products, fp32-faithful)"
-                               if f16_split else
-                               f"{peaks['_source']}: sustained bf16 x 1/2 (tf32) x 1/3 (3xTF32, fp32-faithful)"),
-                "algorithmic_flops_per_patch": 2 * k * d_dim,
-                "algorithmic_bytes_per_patch": 4 * d_dim + 8,
-                "hbm_frac": (4 * d_dim + 8) * n_p / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                "ffma_frac_of_derived_74.4TF": achieved / FFMA_PEAK_TFLOPS,
-                "frac_of_nominal_tf32_pipe": achieved / nominal,
-                "frac_of_measured_tcgen05_tf32_peak": (achieved / pipe_peak) if pipe_peak else None,
-                "measured_tcgen05_tf32_peak_3x": pipe_peak,
-                "tensor_pipe_active_pct_ncu": pipe_pct,
-                "note": ("FP16-split mode: 4 MMAs (512 tensor-pipe cycles) per 128x256 tile; the pace is set by the "
-                         "epilogue's min-reduction on the half-rate ALU pipe (~850 cycles per tile, 547 with the "
-                         "reduction switched off: DESIGN 5), so frac is against a roof this kernel does not bind on; "
-                         "SOM_TC_S_F16=0 selects the 3xTF32 mode (7 MMAs per tile, tensor pipe 94% active)"
-                         if f16_split else
-                         "frac > 1 is expected: the denominator is the measured sustained cuBLAS bf16 rate / 6; "
-                         "the kernel keeps the tensor pipe ~94% active (ncu) and is bounded by the SM clock "
-                         "under the power cap (1.55-1.65 GHz).  Against the tensor pipe's own measured sustained "
-                         "TF32 rate (930 TFLOP/s dense = 310 fp32-faithful) see frac_of_measured_tcgen05_tf32_peak; "
-                         "7 MMAs per tile carry 6 MMAs of useful products (K' = 56 for 3*16)")}
-
-    extra = None
+    extra = {}
     if not args.no_extra:
+        if world > 1:
+            try:
+                extra["checks"] = run_checks(tr, cb, dev, world, rank)
+            except Exception as e:  # noqa: BLE001
+                extra["checks"] = {"error": repr(e), "all_ok": False}
+        del tr, cb, xs
+        torch.cuda.empty_cache()
         try:
-            del host, out_host, tok
-            extra = _extra_training(dev, world, rank, None)
+            extra["C5_sharded_search"] = extra_c5(dev, world, rank)
         except Exception as e:  # noqa: BLE001
-            extra = {"error": repr(e)}
-
-    if extra is not None and world == 1 and not args.no_extra:
-        try:
-            torch.cuda.empty_cache()
-            extra["other_configs"] = _extra_configs(dev)
-        except Exception as e:  # noqa: BLE001
-            extra["other_configs"] = {"error": repr(e)}
+            extra["C5_sharded_search"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+        if world == 1:
+            for name, fn in (("C2_bmu", lambda: extra_c2(dev, peaks)), ("small_configs", lambda: extra_small_configs(dev))):
+                try:
+                    extra[name] = fn()
+                except Exception as e:  # noqa: BLE001
+                    extra[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = _cpu_reference_bmu(steps=4, warmup=1, min_seconds=10.0)
+        cpu_base, _ = _cpu_reference_step(steps=3, warmup=1, min_seconds=10.0)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1] (C2): 39 063 synthetic 4x32x32 fmaps, P=2 (D=16), "
-                                       "K=4096 trained-like codebook, 10 000 128 patches per GPU per step, BMU only",
-                           "l2": "per-step input 640 MB + 80 MB of indices exceed the 126 MB L2",
-                           "variant": int(variant), "patches_per_gpu": n_p},
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_base, "extra": extra}
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (BMU: fp16 hi/lo split x3 products on tcgen05, fp32 accumulate; update, filters and Adam "
+                         "fp32; filters 3xTF32)",
+                "data": "synthetic", "config": CONFIG, "details": head["details"], "loss": head["loss"],
+                "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+                "roofline": head["roofline"], "breakdown": head["breakdown"], "cpu_baseline": cpu_base,
+                "extra": extra or None}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

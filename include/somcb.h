@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SOM_ABI_VERSION 1
+#define SOM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SOM_API __attribute__((visibility("default")))
@@ -54,10 +54,15 @@ extern "C" {
 /* BMU kernel variants (static rule in som_bmu_pick_variant; no runtime autotuner) */
 #define SOM_BMU_AUTO         0
 #define SOM_BMU_FFMA         1   /* fp32 FFMA register-tiled kernel, any shape                  */
-#define SOM_BMU_TC3X         2   /* tcgen05, error-compensated hi/lo split (3 products), TMEM argmin:
-                                  * kind::tf32 3xTF32; for D <= 16 and >= 65 536 patches a kind::f16 FP16
-                                  * split with exact power-of-two scaling (same 11+11-bit operand precision,
-                                  * fp32 accumulation; environment SOM_TC_S_F16=0 keeps 3xTF32 everywhere)  */
+#define SOM_BMU_TC3X         2   /* tcgen05, error-compensated hi/lo split (3 products), TMEM argmin.  The split
+                                  * arithmetic follows a static rule on the shape (som_bmu_split_mode): kind::tf32
+                                  * 3xTF32, or -- large batches: D <= 16 from 65 536 patches, 16 < D <= 256 from one
+                                  * full wave of 128-patch tiles -- a kind::f16 FP16 hi/lo split with exact
+                                  * power-of-two scaling (same 11+11-bit operand precision, fp32 accumulation)       */
+#define SOM_BMU_TC_TF32      3   /* SOM_BMU_TC3X with the 3xTF32 arithmetic at every size                            */
+#define SOM_BMU_TC_F16       4   /* SOM_BMU_TC3X with the FP16 split at every size (SOM_E_UNSUPPORTED when no FP16
+                                  * kernel covers the shape: D > 256 or fewer than 513 units); near-tie picks may
+                                  * differ between the arithmetics within the 1e-6 relative distance rule            */
 
 SOM_API int         som_version(void);
 SOM_API const char* som_last_error(void);
@@ -80,6 +85,9 @@ SOM_API int som_prepare_codebook_f32(const float* W, int K, int D, float* c_norm
  * unit_offset / out_rd serve the unit-sharded mode (som_merge_candidates).              */
 SOM_API size_t som_bmu_workspace_bytes(int64_t n_patches, int D, int K, int variant);
 SOM_API int    som_bmu_pick_variant(int64_t n_patches, int D, int K);
+/* Split arithmetic the static rule picks for this shape: 1 = FP16 hi/lo (kind::f16), 0 = 3xTF32, -1 = not a
+ * tensor-core shape (FFMA variant).  Host-only, no device work.                                              */
+SOM_API int    som_bmu_split_mode(int64_t n_patches, int D, int K);
 SOM_API int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
                      const float* W, const float* c_norm2, int K, int64_t unit_offset,
                      int64_t* out_idx, float* out_rd,
@@ -133,6 +141,15 @@ SOM_API int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int H,
                             float* Rbar, int64_t* counts, double* sse,
                             void* ws, size_t ws_bytes, void* stream);
 
+/* Data-parallel form of K2 (train_codebook.py:225-249 sharded over ranks; the reference has no counterpart):
+ * `packed` holds K*D + 4 floats = [ Rbar | sse_hi, sse_lo, n/4096, n%4096 ] -- the fp64 squared error as a float
+ * pair and the LOCAL patch count n as two exactly representable floats -- so that ONE fp32 all-reduce(sum) of the
+ * buffer carries the accumulators, the loss numerator and the global batch size (ragged shares allowed; an empty
+ * share, n_img == 0, zero-fills).  Wt must not be NULL.  Same workspace as som_accumulate_nchw_f32.        */
+SOM_API int som_accumulate_packed_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                                   const int64_t* bmu, const float* Wt, int K,
+                                   float* packed, void* ws, size_t ws_bytes, void* stream);
+
 /* Autograd backward of the quantise gather (drop-in path): Rbar[a] = sum_{p: bmu[p]==a} patchify(grad_out)[p]
  * -- the segment sum the reference's S^T @ grad reduces to after S = onehot(bmu) @ T; follow it
  * with som_filter_f32(scale = 1) to obtain grad_W (autograd of models/Codebook.py:128-130).
@@ -159,6 +176,15 @@ SOM_API int som_adam_f32(float* W, float* m, float* v, const float* g, int64_t n
  * step): uses t = *steps_done + 1, then increments *steps_done on the stream.               */
 SOM_API int som_adam_devstep_f32(float* W, float* m, float* v, const float* g, int64_t n,
                          double lr, double b1, double b2, double eps, int64_t* steps_done, void* stream);
+
+/* Data-parallel tail of the step: `g` is the UNSCALED gradient T @ Rbar_global (som_filter_ws_f32 with scale 1 on
+ * the all-reduced accumulators) and `tail` the all-reduced 4-float tail of som_accumulate_packed_nchw_f32.  Applies
+ * g * (float)(2 / numel), numel = D * n_global (F.mse_loss's mean, train_codebook.py:233-235) and the Adam rule of
+ * som_adam_devstep_f32; writes loss = sse / numel to loss_out (device double, may be NULL).  Everything the host
+ * would have to wait for stays on the device, so the whole step can be captured in a CUDA graph.            */
+SOM_API int som_adam_dp_f32(float* W, float* m, float* v, const float* g, int64_t n, int D,
+                    double lr, double b1, double b2, double eps, int64_t* steps_done,
+                    const float* tail, double* loss_out, void* stream);
 
 /* ---- row compaction for pruning ----------------------------------------------------------
  * out[r] = W[keep[r]] for r < n_keep (prune_codebook.py:161-162).                        */

@@ -366,9 +366,12 @@ acc_scan_kernel(const float* __restrict__ x, Geom g, const int64_t* __restrict__
     }
 }
 
-// fixed-order double reduction of the per-(chunk, slice) squared-error partials
+// fixed-order double reduction of the per-(chunk, slice) squared-error partials.  `tail` (data-parallel form, may be
+// NULL) receives [sse_hi, sse_lo, n / 4096, n % 4096] as floats: the fp64 sum as a float pair and the local patch
+// count as two exactly representable floats, so that ONE fp32 all-reduce(sum) of [Rbar | tail] carries them too.
 __global__ void __launch_bounds__(1024) sse_reduce_kernel(const double* __restrict__ part, int64_t m,
-                                                          double* __restrict__ out) {
+                                                          double* __restrict__ out, float* __restrict__ tail,
+                                                          int64_t n_patches) {
     __shared__ double sh[1024];
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < m; i += 1024) s += part[i];
@@ -378,20 +381,29 @@ __global__ void __launch_bounds__(1024) sse_reduce_kernel(const double* __restri
         if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = sh[0];
+    if (threadIdx.x == 0) {
+        if (out != nullptr) *out = sh[0];
+        if (tail != nullptr) {
+            const float hi = (float)sh[0];
+            tail[0] = hi;
+            tail[1] = (float)(sh[0] - (double)hi);
+            tail[2] = (float)(n_patches >> 12);
+            tail[3] = (float)(n_patches & 4095);
+        }
+    }
 }
 
 template <int VEC>
 static int launch_levels(const float* x, const Geom& g, const AccumPlan& pl, const int* skey,
                          const int* sid, const int* offsets, const float* Wt, float* Rbar,
-                         int64_t* counts, double* sse, float* partial, double* sse_part,
+                         int64_t* counts, double* sse, float* tail, float* partial, double* sse_part,
                          cudaStream_t st) {
     const int n_slices = (int)ceil_div64(g.D, 32 * VEC);
     if (pl.n_chunks > 0) {
         int64_t warps = pl.n_chunks * n_slices;
         unsigned blocks = (unsigned)ceil_div64(warps, ACC_WARPS);
         seg_level1_kernel<VEC><<<blocks, ACC_WARPS * 32, 0, st>>>(
-            x, g, skey, sid, offsets, Wt, Rbar, partial, (sse && Wt) ? sse_part : nullptr,
+            x, g, skey, sid, offsets, Wt, Rbar, partial, ((sse || tail) && Wt) ? sse_part : nullptr,
             pl.S, pl.n_chunks, n_slices);
         int rc = check_launch("seg_level1_kernel");
         if (rc) return rc;
@@ -404,9 +416,9 @@ static int launch_levels(const float* x, const Geom& g, const AccumPlan& pl, con
         int rc = check_launch("seg_level2_kernel");
         if (rc) return rc;
     }
-    if (sse != nullptr) {
+    if (sse != nullptr || tail != nullptr) {
         int64_t m = (Wt != nullptr) ? pl.n_chunks * n_slices : 0;
-        sse_reduce_kernel<<<1, 1024, 0, st>>>(sse_part, m, sse);
+        sse_reduce_kernel<<<1, 1024, 0, st>>>(sse_part, m, sse, tail, g.n_patches);
         return check_launch("sse_reduce_kernel");
     }
     return SOM_OK;
@@ -422,11 +434,12 @@ extern "C" size_t som_accumulate_workspace_bytes(int64_t n_patches, int D, int K
     return pl.total;
 }
 
-extern "C" int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH,
-                                       int pW, const int64_t* bmu, const float* Wt, int K,
-                                       float* Rbar, int64_t* counts, double* sse,
-                                       void* ws, size_t ws_bytes, void* stream) {
-    SOM_REQUIRE(x && bmu && Rbar, SOM_E_BADARG, "accumulate: null pointer");
+static int accumulate_impl(const float* x, int64_t n_img, int C, int H, int Wd, int pH,
+                           int pW, const int64_t* bmu, const float* Wt, int K,
+                           float* Rbar, int64_t* counts, double* sse, float* tail,
+                           void* ws, size_t ws_bytes, void* stream) {
+    // an empty (ragged data-parallel) share is valid: Rbar is zero-filled, the tail carries zeros
+    SOM_REQUIRE(Rbar && ((x && bmu) || n_img == 0), SOM_E_BADARG, "accumulate: null pointer");
     SOM_REQUIRE(K > 0, SOM_E_BADARG, "accumulate: K=%d", K);
     Geom g;
     int rc = make_geom(&g, x, n_img, C, H, Wd, pH, pW);
@@ -458,14 +471,14 @@ extern "C" int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int
         if (((uintptr_t)Rbar & 15) != 0) vec = 1;
         const int n_slices = (int)ceil_div64(g.D, (int64_t)SCAN_THREADS * vec);
         dim3 grid((unsigned)K, (unsigned)n_slices);
-        double* sp = (sse && Wt) ? sse_part : nullptr;
+        double* sp = ((sse || tail) && Wt) ? sse_part : nullptr;
         if (vec == 4) acc_scan_kernel<4><<<grid, SCAN_THREADS, 0, st>>>(x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
         else if (vec == 2) acc_scan_kernel<2><<<grid, SCAN_THREADS, 0, st>>>(x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
         else acc_scan_kernel<1><<<grid, SCAN_THREADS, 0, st>>>(x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
         rc = check_launch("acc_scan_kernel");
         if (rc) return rc;
-        if (sse != nullptr) {
-            sse_reduce_kernel<<<1, 1024, 0, st>>>(sse_part, (Wt != nullptr) ? (int64_t)K * n_slices : 0, sse);
+        if (sse != nullptr || tail != nullptr) {
+            sse_reduce_kernel<<<1, 1024, 0, st>>>(sse_part, (Wt != nullptr) ? (int64_t)K * n_slices : 0, sse, tail, n);
             return check_launch("sse_reduce_kernel");
         }
         return SOM_OK;
@@ -493,9 +506,25 @@ extern "C" int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int
     if (((uintptr_t)Rbar & 15) != 0) vec = 1;
     // a warp covers 32 * vec features of one patch row: keep all lanes busy for short rows (C4, D = 64: vec 2)
     while (vec > 1 && 32 * vec > g.D) vec >>= 1;
-    if (vec == 4) return launch_levels<4>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
-    if (vec == 2) return launch_levels<2>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
-    return launch_levels<1>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, partial, sse_part, st);
+    if (vec == 4) return launch_levels<4>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, tail, partial, sse_part, st);
+    if (vec == 2) return launch_levels<2>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, tail, partial, sse_part, st);
+    return launch_levels<1>(x, g, pl, skey, sid, offsets, Wt, Rbar, counts, sse, tail, partial, sse_part, st);
+}
+
+extern "C" int som_accumulate_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH,
+                                       int pW, const int64_t* bmu, const float* Wt, int K,
+                                       float* Rbar, int64_t* counts, double* sse,
+                                       void* ws, size_t ws_bytes, void* stream) {
+    return accumulate_impl(x, n_img, C, H, Wd, pH, pW, bmu, Wt, K, Rbar, counts, sse, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int som_accumulate_packed_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH,
+                                              int pW, const int64_t* bmu, const float* Wt, int K,
+                                              float* packed, void* ws, size_t ws_bytes, void* stream) {
+    SOM_REQUIRE(packed && Wt, SOM_E_BADARG, "accumulate(packed): null pointer");
+    const int64_t kd = (int64_t)K * C * pH * pW;
+    return accumulate_impl(x, n_img, C, H, Wd, pH, pW, bmu, Wt, K, packed, nullptr, nullptr, packed + kd, ws, ws_bytes,
+                           stream);
 }
 
 extern "C" int som_backward_nchw_f32(const float* grad_out, int64_t n_img, int C, int H, int Wd, int pH, int pW,

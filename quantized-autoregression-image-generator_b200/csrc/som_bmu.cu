@@ -9,13 +9,24 @@ int launch_bmu_ffma(const float* x, const Geom& g, const float* W, const float* 
                     cudaStream_t st);
 // som_bmu_tc.cu
 bool tc_supported(int64_t n_patches, int D, int K);
-size_t tc_workspace_bytes(int64_t n_patches, int D, int K);
+size_t tc_workspace_bytes(int64_t n_patches, int D, int K, int arith);
+int tc_split_mode(int64_t n_patches, int D, int K, int arith);
 int launch_bmu_tc(const float* x, const Geom& g, const float* W, const float* cn, int K,
-                  int64_t unit_offset, int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes,
+                  int64_t unit_offset, int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, int arith,
                   cudaStream_t st);
 }  // namespace som
 
 using namespace som;
+
+// tensor-core variants -> arithmetic selector of som_bmu_tc.cu (0 static rule, 1 3xTF32, 2 FP16 split)
+static inline bool is_tc(int variant) { return variant >= SOM_BMU_TC3X && variant <= SOM_BMU_TC_F16; }
+static inline int arith_of(int variant) { return variant == SOM_BMU_TC_TF32 ? 1 : (variant == SOM_BMU_TC_F16 ? 2 : 0); }
+
+extern "C" int som_bmu_split_mode(int64_t n_patches, int D, int K) {
+    if (n_patches <= 0 || D <= 0 || K <= 0) return -1;
+    if (som_bmu_pick_variant(n_patches, D, K) != SOM_BMU_TC3X) return -1;
+    return tc_split_mode(n_patches, D, K, 0);
+}
 
 extern "C" int som_bmu_pick_variant(int64_t n_patches, int D, int K) {
     // Static rule on the shape (no runtime autotuner), from the measured crossovers of tools/crossover.py:
@@ -34,7 +45,7 @@ extern "C" int som_bmu_pick_variant(int64_t n_patches, int D, int K) {
 extern "C" size_t som_bmu_workspace_bytes(int64_t n_patches, int D, int K, int variant) {
     if (n_patches <= 0 || D <= 0 || K <= 0) return 0;
     if (variant == SOM_BMU_AUTO) variant = som_bmu_pick_variant(n_patches, D, K);
-    if (variant == SOM_BMU_TC3X) return tc_workspace_bytes(n_patches, D, K);
+    if (is_tc(variant)) return tc_workspace_bytes(n_patches, D, K, arith_of(variant));
     return ffma_workspace_bytes(n_patches, K);
 }
 
@@ -46,16 +57,16 @@ extern "C" int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int
     // returns an empty int64 tensor for it (models/Codebook.py:77-99 on a (0, C, H, W) input)
     SOM_REQUIRE(W && c_norm2 && ((x && out_idx) || n_img == 0), SOM_E_BADARG, "bmu: null pointer");
     SOM_REQUIRE(K > 0, SOM_E_BADARG, "bmu: K=%d", K);
-    SOM_REQUIRE(variant >= SOM_BMU_AUTO && variant <= SOM_BMU_TC3X, SOM_E_BADARG, "bmu: variant=%d", variant);
+    SOM_REQUIRE(variant >= SOM_BMU_AUTO && variant <= SOM_BMU_TC_F16, SOM_E_BADARG, "bmu: variant=%d", variant);
     Geom g;
     int rc = make_geom(&g, x, n_img, C, H, Wd, pH, pW);
     if (rc) return rc;
     if (g.n_patches == 0) return SOM_OK;
     if (variant == SOM_BMU_AUTO) variant = som_bmu_pick_variant(g.n_patches, g.D, K);
-    if (variant == SOM_BMU_TC3X) {
+    if (is_tc(variant)) {
         SOM_REQUIRE(tc_supported(g.n_patches, g.D, K), SOM_E_UNSUPPORTED,
                     "bmu: tensor-core variant does not support D=%d K=%d", g.D, K);
-        return launch_bmu_tc(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes,
+        return launch_bmu_tc(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes, arith_of(variant),
                              (cudaStream_t)stream);
     }
     return launch_bmu_ffma(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes,

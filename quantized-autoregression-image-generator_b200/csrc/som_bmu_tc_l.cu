@@ -614,11 +614,15 @@ __global__ void __launch_bounds__(256) split_w_l_kernel(const float* __restrict_
 
 // CTA pairs (cta_group::2).  Static rule: pairs when there is no feature split and at least two waves of patch
 // tiles (measured: C4 7.44 -> 7.23 ms, C5 64.1 -> 62.1 ms; split-K shapes are faster unpaired).
-// SOM_TC_PAIR=0 / 1 forces the choice for A/B runs (read once per process).
+// Experiment builds (-DSOM_TC_EXPERIMENTS) read SOM_TC_PAIR=0 / 1 to force the choice for A/B runs.
 static int pair_mode() {
+#ifdef SOM_TC_EXPERIMENTS
     static int mode = -2;
     if (mode == -2) { const char* e = getenv("SOM_TC_PAIR"); mode = e ? atoi(e) : -1; }
     return mode;
+#else
+    return -1;
+#endif
 }
 
 // streamed mode pre-pass: patch rows p0 .. p0+rows-1 -> [ hi(x) for every 32-feature block | lo(x) for every block ],

@@ -642,15 +642,13 @@ size_t tc_s_workspace_bytes(int64_t n_patches, int D, int K) {
 
 // Split mode of the config-S kernel.  Static rule: FP16 from 65 536 patches on (C2: 4.1-4.3 vs 4.8-4.9 ms); below that
 // a launch is tens of microseconds and the extra scale pre-pass (one CTA, a few us) would eat the gain, so small batches
-// keep the 3xTF32 mode.  SOM_TC_S_F16 = 1 / 0 forces FP16 / TF32 for every size (read once per process; tests, A/B).
-static bool tc_s_f16_mode(int64_t n_patches) {
-    static int mode = -2;
-    if (mode == -2) { const char* e = getenv("SOM_TC_S_F16"); mode = e ? (atoi(e) != 0) : -1; }
-    return mode < 0 ? n_patches >= 65536 : mode != 0;
+// keep the 3xTF32 mode.  The caller's variant (SOM_BMU_TC_TF32 / SOM_BMU_TC_F16) forces one arithmetic for every size.
+bool tc_s_f16_mode(int64_t n_patches, int arith) {
+    return arith == 0 ? n_patches >= 65536 : arith == 2;
 }
 
 int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
-                    int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, int arith, cudaStream_t st) {
     using namespace tcs;
     const int64_t n = g.n_patches;
     if (n == 0) return SOM_OK;
@@ -663,7 +661,7 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
     float* Bp = (float*)ws;
     float* Tp = (float*)((char*)ws + align_up((size_t)K_pad * 32 * 4, 1024));
     float* scale = (float*)((char*)Tp + align_up((size_t)K_pad * 8 * 4, 1024));
-    const bool f16 = tc_s_f16_mode(n);
+    const bool f16 = tc_s_f16_mode(n, arith);
     if (f16) {
         cb_scale_kernel<<<1, 1024, 0, st>>>(W, cn, K, D, scale);
         int rc = check_launch("cb_scale_kernel");

@@ -491,6 +491,49 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ W, fl
 }
 __global__ void step_bump_kernel(int64_t* steps_done) { *steps_done += 1; }
 
+// Data-parallel tail: the gradient arrives UNSCALED (g = T @ Rbar_global) and the global batch size is only known on
+// the device, from the all-reduced tail [sse_hi, sse_lo, n / 4096, n % 4096] (som_accumulate_packed_nchw_f32):
+// g_eff = g * (float)(2 / numel), numel = D * n_global -- the same single rounding as the filter's own `scale * acc`
+// epilogue, so the result is bit-identical to the host-scaled path; thread 0 also writes the mean squared error.
+__global__ void __launch_bounds__(256) adam_dp_kernel(float* __restrict__ W, float* __restrict__ m,
+                                                      float* __restrict__ v, const float* __restrict__ g,
+                                                      int64_t n, int D, double lr, double b1, double b2, float eps,
+                                                      const int64_t* __restrict__ steps_done,
+                                                      const float* __restrict__ tail, double* __restrict__ loss_out) {
+    const double t = (double)(*steps_done + 1);
+    const double numel = ((double)tail[2] * 4096.0 + (double)tail[3]) * (double)D;
+    const float gscale = (float)(2.0 / numel);
+    AdamScalars a;
+    a.w1 = (float)(1.0 - b1); a.b2 = (float)b2; a.one_m_b2 = (float)(1.0 - b2);
+    a.step_size = (float)(lr / (1.0 - pow(b1, t)));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow(b2, t));
+    a.eps = eps;
+    if (loss_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        *loss_out = ((double)tail[0] + (double)tail[1]) / numel;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool al = ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(m) |
+                      reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+    const int64_t n4 = al ? n / 4 : 0;
+    float4* W4 = reinterpret_cast<float4*>(W);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int64_t q = tid; q < n4; q += stride) {
+        float4 gq = __ldcs(g4 + q), mq = m4[q], vq = v4[q], wq = W4[q];
+        adam_update(a, gq.x * gscale, mq.x, vq.x, wq.x);
+        adam_update(a, gq.y * gscale, mq.y, vq.y, wq.y);
+        adam_update(a, gq.z * gscale, mq.z, vq.z, wq.z);
+        adam_update(a, gq.w * gscale, mq.w, vq.w, wq.w);
+        W4[q] = wq; m4[q] = mq; v4[q] = vq;
+    }
+    for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
+        float mi = m[i], vi = v[i], wi = W[i];
+        adam_update(a, g[i] * gscale, mi, vi, wi);
+        W[i] = wi; m[i] = mi; v[i] = vi;
+    }
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ W, int D,
                                                           const int64_t* __restrict__ keep,
                                                           int64_t n_keep, float* __restrict__ out) {
@@ -713,6 +756,22 @@ int som_adam_devstep_f32(float* W, float* m, float* v, const float* g, int64_t n
         int blocks = grid_for(n, 256 * 4, 8);
         adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, m, v, g, n, lr, b1, b2, (float)eps, steps_done);
         int rc = check_launch("adam_dev_kernel");
+        if (rc) return rc;
+    }
+    step_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(steps_done);
+    return check_launch("step_bump_kernel");
+}
+
+int som_adam_dp_f32(float* W, float* m, float* v, const float* g, int64_t n, int D,
+                    double lr, double b1, double b2, double eps, int64_t* steps_done,
+                    const float* tail, double* loss_out, void* stream) {
+    SOM_REQUIRE(W && m && v && g && steps_done && tail, SOM_E_BADARG, "adam(dp): null pointer");
+    SOM_REQUIRE(n >= 0 && D > 0, SOM_E_BADARG, "adam(dp): n=%lld D=%d", (long long)n, D);
+    if (n > 0) {
+        int blocks = grid_for(n, 256 * 4, 8);
+        adam_dp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, m, v, g, n, D, lr, b1, b2, (float)eps, steps_done,
+                                                                tail, loss_out);
+        int rc = check_launch("adam_dp_kernel");
         if (rc) return rc;
     }
     step_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(steps_done);

@@ -219,6 +219,29 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_F16), "r"(accum)
         : "memory");
 }
+// kind::f16 (FP16 operands, fp32 accumulate), M = 128 * CG rows (one 128-row half per CTA), N = 256, K = 16
+template <int CG>
+__device__ __forceinline__ void tc_mma_f16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
+    constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TN >> 3) << 17) |
+                               ((uint32_t)((TM * CG) >> 4) << 24);
+    if (CG == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
 // K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4
 // | version=1 | layout_type=2.  Advancing one K=8 step inside the 128-byte row adds 32 B (2 units).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {

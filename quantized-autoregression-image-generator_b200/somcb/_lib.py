@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsomcb.so")
 
-SOM_BMU_AUTO, SOM_BMU_FFMA, SOM_BMU_TC3X = 0, 1, 2
+SOM_BMU_AUTO, SOM_BMU_FFMA, SOM_BMU_TC3X, SOM_BMU_TC_TF32, SOM_BMU_TC_F16 = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); mirrors include/somcb.h one to one
 SIGNATURES = {
@@ -21,6 +21,7 @@ SIGNATURES = {
     "som_prepare_codebook_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "som_bmu_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "som_bmu_pick_variant": (c_int, [c_int64, c_int, c_int]),
+    "som_bmu_split_mode": (c_int, [c_int64, c_int, c_int]),
     "som_bmu_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_int, c_void_p]),
@@ -38,6 +39,10 @@ SIGNATURES = {
     "som_accumulate_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_size_t, c_void_p]),
+    "som_accumulate_packed_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                               c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "som_adam_dp_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double,
+                                c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "som_quantize_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int,
                                       c_int, c_int, c_void_p, c_void_p]),
     "som_adam_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,

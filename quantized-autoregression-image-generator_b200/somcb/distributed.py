@@ -3,9 +3,11 @@
 Two shardings:
 
 * patch-sharded data parallel (``DataParallelSom``): every rank holds the full codebook and Adam
-  state, takes 1/R of the step's feature maps, runs BMU + per-unit accumulation locally, then
-  ONE all-reduce(sum) of the packed [Rbar (K*D fp32) | SSE (2 fp32)] buffer; filter + Adam are
-  replicated, so replicas stay bit-identical (the all-reduce returns identical bits everywhere).
+  state, takes about 1/R of the step's feature maps (shares may be ragged), runs BMU + per-unit
+  accumulation locally, then ONE all-reduce(sum) of the packed [Rbar (K*D fp32) | SSE (2 fp32) |
+  patch count (2 fp32)] buffer; filter + Adam are replicated, so replicas stay bit-identical (the
+  all-reduce returns identical bits everywhere).  The whole step, collective included, is captured
+  in a CUDA graph (``use_cuda_graph``).
   BMU-only / histogram workloads need no exchange beyond a final all-reduce of K int64 counts.
 * unit-sharded search (``sharded_bmu``): rank r owns units [lo_r, hi_r); patches are replicated;
   each rank returns (reduced distance, global index) candidates from the SAME kernel arithmetic as
@@ -31,12 +33,10 @@ def shard_bounds(total, world_size, rank):
 
 
 def split_batch(feature_map, world_size, rank):
-    """Equal contiguous slice of the batch dimension (DP needs equal shares per rank)."""
-    n = feature_map.shape[0]
-    if n % world_size:
-        raise ValueError(f"batch {n} is not divisible by world size {world_size}")
-    per = n // world_size
-    return feature_map[rank * per:(rank + 1) * per]
+    """Contiguous near-equal slice of the batch dimension for ``rank``.  Shares may be ragged (and empty when there
+    are fewer feature maps than ranks): the step all-reduces the patch count next to the accumulators."""
+    lo, hi = shard_bounds(feature_map.shape[0], world_size, rank)
+    return feature_map[lo:hi]
 
 
 class DataParallelSom(SomTrainer):

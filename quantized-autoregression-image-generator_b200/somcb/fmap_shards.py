@@ -123,6 +123,16 @@ class ShardReader:
         self.pin = bool(pin) and torch.cuda.is_available()
         self.depth = int(depth)
         self._bufs = None
+        self._busy = {}               # staging slot -> CUDA event of the last asynchronous consumer
+        self._last_slot = None
+
+    def mark_in_flight(self, event):
+        """Tell the reader that the batch yielded LAST is still being read asynchronously (e.g. by a non-blocking
+        host-to-device copy); ``event`` is a ``torch.cuda.Event`` recorded after that work.  The staging slot is not
+        refilled before the event has completed.  Consumers that finish with a batch before asking for the next one
+        (``HostTokenizer.tokenize(..., sync=True)``) need not call this."""
+        if self._last_slot is not None:
+            self._busy[self._last_slot] = event
 
     def __len__(self):
         return sum(self.counts)
@@ -154,8 +164,13 @@ class ShardReader:
             mm = self._map(i)
             for a in range(0, n, self.batch):
                 b = min(n, a + self.batch)
-                buf = self._bufs[k % self.depth]
+                slot = k % self.depth
+                ev = self._busy.pop(slot, None)
+                if ev is not None:
+                    ev.synchronize()              # an earlier DMA out of this pinned slot is still pending
+                buf = self._bufs[slot]
                 buf[:b - a].numpy()[...] = mm[a:b]
+                self._last_slot = slot
                 yield lo + a, lo + b, buf[:b - a]
                 k += 1
             lo += n

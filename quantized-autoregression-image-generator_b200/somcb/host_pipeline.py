@@ -51,6 +51,7 @@ class HostTokenizer:
             raise RuntimeError("HostTokenizer needs the codebook on a CUDA device (no CPU fallback)")
         self.device = w.device
         self._bufs = None
+        self.done = None
 
     def _alloc(self, c, h, w, seq):
         key = (c, h, w, seq)
@@ -69,9 +70,14 @@ class HostTokenizer:
         return self._bufs[1]
 
     @torch.no_grad()
-    def tokenize(self, fmaps_host, out_host=None):
+    def tokenize(self, fmaps_host, out_host=None, sync=True):
         """fmaps_host: (N, C, H, W) fp32 host tensor (pinned for async copies).  Returns the
-        (N, Seq) int64 host tensor of BMU indices (``out_host`` if given, pinned otherwise)."""
+        (N, Seq) int64 host tensor of BMU indices (``out_host`` if given, pinned otherwise).
+
+        With ``sync=True`` (default) the call returns only after the last device-to-host copy has landed and the
+        last host-to-device copy has been read: the returned indices are valid and ``fmaps_host`` may be refilled.
+        With ``sync=False`` the copies may still be in flight on return; wait on ``self.done`` (a CUDA event covering
+        both copy streams) -- ``self.done.synchronize()`` -- before touching either host buffer."""
         cb = self.cb
         n, c, h, w = fmaps_host.shape
         geom1 = _ops.geometry((1, c, h, w), cb.patch_dim)
@@ -108,4 +114,77 @@ class HostTokenizer:
                 sl["d2h"].record(s_out)
         compute.wait_stream(s_out)
         compute.wait_stream(s_in)
+        self.done = torch.cuda.Event()
+        self.done.record(compute)
+        if sync:
+            # wait_stream only orders GPU streams; the HOST must not read out_host (or refill fmaps_host) earlier
+            self.done.synchronize()
         return out_host
+
+
+class PendingLoss:
+    """Loss of an enqueued step: a pinned host scalar that becomes valid when ``event`` has completed."""
+
+    def __init__(self, host, event):
+        self.host, self.event = host, event
+
+    def item(self):
+        self.event.synchronize()
+        return float(self.host)
+
+
+class HostTrainer:
+    """SOM training from HOST batches: what the loop of train_codebook.py:216-249 does per step (the DataLoader's
+    batch arrives in host memory, ``.to(device)``, step, ``loss.item()``), as a pipeline over ``depth`` device staging
+    buffers: the host-to-device copy of batch i+1 runs on a copy stream while step i computes, the step itself is
+    the trainer's CUDA graph captured on the staging buffer (``use_cuda_graph="alias"``), and the loss comes back
+    through a pinned scalar.  ``trainer`` is a SomTrainer / DataParallelSom; under data parallelism every rank
+    feeds its own share."""
+
+    def __init__(self, trainer, depth=2):
+        self.tr = trainer
+        self.depth = int(depth)
+        w = trainer.cb.codebook.weight
+        if not w.is_cuda:
+            raise RuntimeError("HostTrainer needs the codebook on a CUDA device (no CPU fallback)")
+        self.device = w.device
+        self._slots = None
+        self._i = 0
+        self._copy = torch.cuda.Stream(self.device)
+
+    def _alloc(self, shape):
+        if self._slots is not None and self._slots[0] == tuple(shape):
+            return self._slots[1]
+        slots = [{"x": torch.empty(shape, dtype=torch.float32, device=self.device),
+                  "loss": torch.empty((), dtype=torch.float64, pin_memory=True),
+                  "h2d": torch.cuda.Event(), "done": None} for _ in range(self.depth)]
+        self._slots = (tuple(shape), slots)
+        return slots
+
+    @torch.no_grad()
+    def step(self, fmaps_host):
+        """Enqueue copy + step for one (local) host batch (pinned for asynchronous copies); returns a PendingLoss.
+        ``fmaps_host`` may be refilled once ``h2d_done()`` of this call has completed (or after the loss is read)."""
+        slots = self._alloc(fmaps_host.shape)
+        sl = slots[self._i % self.depth]
+        self._i += 1
+        compute = torch.cuda.current_stream(self.device)
+        if sl["done"] is not None:
+            self._copy.wait_event(sl["done"])         # the step that last read this staging buffer
+        else:
+            self._copy.wait_stream(compute)
+        with torch.cuda.stream(self._copy):
+            sl["x"].copy_(fmaps_host, non_blocking=True)
+            sl["h2d"].record(self._copy)
+        compute.wait_event(sl["h2d"])
+        loss = self.tr.step(sl["x"])
+        sl["loss"].copy_(loss, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(compute)
+        sl["done"] = done
+        self.last_h2d = sl["h2d"]
+        return PendingLoss(sl["loss"], done)
+
+    def h2d_done(self):
+        """Event after which the host batch of the LAST step() call has been read completely."""
+        return self.last_h2d

@@ -8,7 +8,7 @@ CPU tensors -- there is no fallback path.
 import torch
 
 from . import _lib
-from ._lib import SOM_BMU_AUTO, SOM_BMU_FFMA, SOM_BMU_TC3X, check  # noqa: F401
+from ._lib import SOM_BMU_AUTO, SOM_BMU_FFMA, SOM_BMU_TC3X, SOM_BMU_TC_TF32, SOM_BMU_TC_F16, check  # noqa: F401
 
 
 REQUIRES_CUDA = True
@@ -185,6 +185,50 @@ def accumulate(x, geom, bmu_idx, table, num_units, want_counts=False, want_sse=F
                                           _ptr(out), _ptr(counts), _ptr(sse), _ptr(ws), ws_bytes,
                                           _stream(x)))
     return out, counts, sse
+
+
+def accumulate_packed(x, geom, bmu_idx, table, num_units, packed=None, ws=None):
+    """K2, data-parallel form.  ``packed``: (K*D + 4,) fp32 = [Rbar | sse_hi, sse_lo, n/4096, n%4096] (see
+    include/somcb.h); allocated when not given.  ``ws``: optional caller-kept workspace (uint8)."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    bmu_idx = _req(bmu_idx, torch.int64, "bmu")
+    table = _req(table, torch.float32, "table")
+    d = dim_of(geom)
+    npat = n_patches_of(geom)
+    if bmu_idx.numel() != npat:
+        raise ValueError("bmu does not match the geometry")
+    if packed is None:
+        packed = torch.empty(num_units * d + 4, dtype=torch.float32, device=x.device)
+    packed = _req(packed, torch.float32, "packed")
+    if packed.numel() != num_units * d + 4:
+        raise ValueError("packed must hold K*D + 4 floats")
+    with torch.cuda.device(x.device):
+        need = lib.som_accumulate_workspace_bytes(npat, d, int(num_units))
+        if ws is None or ws.numel() < need:
+            ws, _ = _workspace(need, x.device)
+        check("som_accumulate_packed_nchw_f32",
+              lib.som_accumulate_packed_nchw_f32(_ptr(x), *geom, _ptr(bmu_idx), _ptr(table), int(num_units),
+                                                 _ptr(packed), _ptr(ws), ws.numel(), _stream(x)))
+    return packed
+
+
+def adam_step_dp(weight, m, v, grad, dim, lr, steps_done, tail, loss_out=None, betas=(0.5, 0.999), eps=1e-8):
+    """K4, data-parallel tail: ``grad`` unscaled (T @ Rbar_global), ``tail`` the all-reduced 4-float tail of
+    ``accumulate_packed``; scales by 2 / numel on the device, writes the loss, increments ``steps_done``."""
+    lib = _lib.load()
+    for t, nm in ((weight, "weight"), (m, "m"), (v, "v"), (grad, "grad"), (tail, "tail")):
+        _req(t, torch.float32, nm)
+    _req(steps_done, torch.int64, "steps_done")
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float64, device=weight.device)
+    _req(loss_out, torch.float64, "loss_out")
+    with torch.cuda.device(weight.device):
+        check("som_adam_dp_f32",
+              lib.som_adam_dp_f32(_ptr(weight), _ptr(m), _ptr(v), _ptr(grad), weight.numel(), int(dim), float(lr),
+                                  float(betas[0]), float(betas[1]), float(eps), _ptr(steps_done), _ptr(tail),
+                                  _ptr(loss_out), _stream(weight)))
+    return loss_out
 
 
 def quantize(idx, table, geom, out=None):

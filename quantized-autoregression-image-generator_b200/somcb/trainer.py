@@ -5,15 +5,17 @@
 backward, Adam(betas=(0.5, 0.999)).step, lr halving, neighbourhood decrease), but through the
 factorised form of SURVEY.md A.3, never materialising the quantised batch or the N x K Gaussian:
 
-    W~   = T @ W                                   som_filter_f32
+    W~   = T @ W                                   som_filter_ws_f32
     bmu  = argmin_j ||x - W_j||                    som_bmu_nchw_f32
-    Rbar = segsum_bmu(W~[bmu] - x), SSE            som_accumulate_nchw_f32
-           (data parallel: one all-reduce of Rbar and SSE here)
-    G    = (2 / numel) * T @ Rbar                  som_filter_f32
-    Adam(W, G)                                     som_adam_f32
+    [Rbar | sse, n] = segsum_bmu(W~[bmu] - x)      som_accumulate_packed_nchw_f32
+           (data parallel: ONE all-reduce of that packed buffer here; ragged shares allowed)
+    G~   = T @ Rbar                                som_filter_ws_f32 (scale 1)
+    Adam(W, (2 / numel) G~), loss = sse / numel    som_adam_dp_f32   (numel from the reduced tail, on the device)
 
-The drop-in ``Codebook`` + torch autograd + torch.optim.Adam path produces the same update; the
-tests check both against the reference's outputs.
+Nothing in the step needs the host: the Adam step count, the global batch size and the loss live in
+device memory, so the whole step -- the NCCL all-reduce included -- is captured into a CUDA graph and
+replayed (``use_cuda_graph``).  The drop-in ``Codebook`` + torch autograd + torch.optim.Adam path
+produces the same update; the tests check both against the reference's outputs.
 """
 import torch
 
@@ -21,20 +23,24 @@ from . import ops as _default_ops
 
 
 class SomTrainer:
+    MAX_GRAPHS = 8
+
     def __init__(self, codebook, lr, neighbourhood_step, lr_step=100000, global_steps=0,
                  betas=(0.5, 0.999), eps=1e-8, ops=None, reduce_fn=None, world_size=1,
-                 use_cuda_graph=False):
-        """``codebook``: a somcb.Codebook on a CUDA device.  ``reduce_fn(list_of_tensors)`` sums
-        tensors in place across data-parallel ranks (None: single device).
+                 use_cuda_graph=False, check_nan=False):
+        """``codebook``: a somcb.Codebook on a CUDA device.  ``reduce_fn(packed)`` sums the packed
+        accumulator buffer in place across data-parallel ranks (None: single device).
 
-        ``use_cuda_graph``: small batches (BASELINE config 1: 512 patches per step) are bound by the
-        ~10 launches of a step, not by the kernels.  With this flag the step is captured once per
-        (batch shape, neighbourhood range, lr) into a CUDA graph and replayed: the batch is copied
-        into a static buffer, Adam's step count lives in device memory (``som_adam_devstep_f32``).
-        ``use_cuda_graph="alias"`` captures on the caller's own input buffer instead of copying into a
-        static one: for loops that refill ONE device staging buffer every step (a changed address forces a
-        re-capture).  Single-device only; the first step always runs eagerly (it performs the one-time
-        kernel attribute set-up that must not happen during capture)."""
+        ``use_cuda_graph``: the step is ~20 launches; small batches (BASELINE config 1: 512 patches per
+        step) and strong-scaled data-parallel shards are bound by them, not by the kernels.  With this
+        flag the step is captured once per (batch shape, neighbourhood range, lr) into a CUDA graph and
+        replayed: the batch is copied into a static buffer first.  ``use_cuda_graph="alias"`` captures on
+        the caller's own input buffer instead (one graph per distinct buffer address, at most MAX_GRAPHS
+        kept): for loops that refill a few device staging buffers.  The first step always runs eagerly
+        (one-time kernel attribute set-up and NCCL communicator creation must not happen during capture).
+
+        ``check_nan``: the reference's ``NaN encountered during training`` guard (train_codebook.py:237-238);
+        it reads the loss back, i.e. one host synchronisation per step, so it is off by default."""
         self.cb = codebook
         self.lr = float(lr)
         self.neighbourhood_step = int(neighbourhood_step)
@@ -45,39 +51,51 @@ class SomTrainer:
         self.ops = ops or _default_ops
         self.reduce_fn = reduce_fn
         self.world_size = int(world_size)
+        self.check_nan = bool(check_nan)
         w = codebook.codebook.weight
         # the reference does not checkpoint Adam state: a resume restarts the moments at zero
         self.m = torch.zeros_like(w, requires_grad=False)
         self.v = torch.zeros_like(w, requires_grad=False)
         self.t = 0
+        # Adam's step count lives on the device (the captured graph and the eager path share it)
+        self.t_dev = torch.zeros(1, dtype=torch.int64, device=w.device)
+        self.packed = torch.empty(w.numel() + 4, dtype=torch.float32, device=w.device)
         self.last_bmu = None
-        self.use_cuda_graph = bool(use_cuda_graph) and reduce_fn is None
+        self.use_cuda_graph = bool(use_cuda_graph)
         self._graph_alias = use_cuda_graph == "alias"
-        self._graph = None            # (key, CUDAGraph, x_static, loss_static, t_dev)
+        self._graphs = {}             # key -> (CUDAGraph, x_static, loss_static)
 
     @torch.no_grad()
     def step(self, feature_map, bmu=None):
         """One training step on a (local) batch; returns the loss as a 0-dim float64 device
         tensor (global mean squared error, as F.mse_loss over the global batch)."""
         if self.use_cuda_graph and bmu is None and self.t >= 1 and feature_map.is_cuda:
-            return self._graph_step(feature_map)
-        return self._eager_step(feature_map, bmu)
+            loss = self._graph_step(feature_map)
+        else:
+            loss = self._eager_step(feature_map, bmu)
+        if self.check_nan and bool(torch.isnan(loss)):
+            raise Exception("NaN encountered during training")
+        return loss
 
     def _graph_step(self, feature_map):
         cb = self.cb
         alias = self._graph_alias and feature_map.is_contiguous() and feature_map.dtype == torch.float32
         key = (tuple(feature_map.shape), float(cb.neighbourhood_range), float(self.lr),
                feature_map.data_ptr() if alias else 0)
-        if self._graph is None or self._graph[0] != key:
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))
             x_static = feature_map if alias else \
                 torch.empty(feature_map.shape, dtype=torch.float32, device=feature_map.device)
-            t_dev = torch.full((1,), self.t, dtype=torch.int64, device=feature_map.device)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(feature_map.device)
-            with torch.cuda.graph(graph):
-                loss_static = self._eager_step(x_static, None, t_dev=t_dev, bookkeeping=False)
-            self._graph = (key, graph, x_static, loss_static, t_dev)
-        _, graph, x_static, loss_static, t_dev = self._graph
+            # thread_local: the NCCL watchdog thread may touch the CUDA API while we capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                loss_static = self._device_step(x_static, None)
+            entry = (graph, x_static, loss_static)
+            self._graphs[key] = entry
+        graph, x_static, loss_static = entry
         if x_static is not feature_map:
             x_static.copy_(feature_map)
         graph.replay()
@@ -85,7 +103,7 @@ class SomTrainer:
         cb._norm_cache = None
         self.last_bmu = None
         self._bookkeeping()
-        return loss_static.clone()
+        return loss_static.clone().reshape(())
 
     def _bookkeeping(self):
         # schedule bookkeeping, in the reference's order (train_codebook.py:247-249, 300-304)
@@ -95,43 +113,36 @@ class SomTrainer:
         if self.global_steps % self.neighbourhood_step == 0:
             self.cb.decrease_neighbourhood(steps=1)
 
-    def _eager_step(self, feature_map, bmu=None, t_dev=None, bookkeeping=True):
+    def _eager_step(self, feature_map, bmu=None):
+        loss = self._device_step(feature_map, bmu)
+        self.t += 1
+        self._bookkeeping()
+        return loss.reshape(())
+
+    def _device_step(self, feature_map, bmu):
+        """Enqueue one step on the current stream (eagerly or under graph capture); returns the (1,) float64
+        device tensor the loss is written to."""
         ops = self.ops
         cb = self.cb
         w = cb.codebook.weight.data
         x, geom = cb._input(feature_map, require_cuda=getattr(ops, 'REQUIRES_CUDA', True))
-        k = cb.num_embeddings
+        k, d = cb.num_embeddings, cb.embedding_dim
         rng = cb.neighbourhood_range
+        kd = k * d
 
         wt = ops.neighbourhood_filter(w, rng)
         if bmu is None:
             bmu = ops.bmu(x, geom, w, ops.prepare_codebook(w), variant=cb.bmu_variant)
-        numel = x.numel() * self.world_size            # every rank holds an equal share
-        if self.reduce_fn is None:
-            rbar, _, sse = ops.accumulate(x, geom, bmu, wt, k, want_sse=True)
-        else:
-            # ONE collective per step: Rbar and the squared error travel in one packed fp32
-            # buffer; the fp64 SSE is carried as a (hi, lo) float pair.
-            kd = k * cb.embedding_dim
-            packed = torch.empty(kd + 2, dtype=torch.float32, device=x.device)
-            rbar = packed[:kd].view(k, cb.embedding_dim)
-            _, _, sse = ops.accumulate(x, geom, bmu, wt, k, want_sse=True, out=rbar)
-            hi = sse.to(torch.float32)
-            packed[kd:kd + 1] = hi
-            packed[kd + 1:kd + 2] = (sse - hi.double()).to(torch.float32)
+        packed = self.packed
+        ops.accumulate_packed(x, geom, bmu, wt, k, packed=packed)
+        if self.reduce_fn is not None:
+            # ONE collective per step: Rbar, the squared error (float pair) and the patch count travel together
             self.reduce_fn(packed)
-            sse = packed[kd:kd + 1].double() + packed[kd + 1:kd + 2].double()
-        grad = ops.neighbourhood_filter(rbar, rng, scale=2.0 / numel)
-        if t_dev is not None:                          # graph capture: step count in device memory
-            ops.adam_step_dev(w, self.m, self.v, grad, self.lr, t_dev, self.betas, self.eps)
-        else:
-            self.t += 1
-            ops.adam_step(w, self.m, self.v, grad, self.lr, self.t, self.betas, self.eps)
+        grad = ops.neighbourhood_filter(packed[:kd].view(k, d), rng, scale=1.0)
+        loss = ops.adam_step_dp(w, self.m, self.v, grad, d, self.lr, self.t_dev, packed[kd:], betas=self.betas,
+                                eps=self.eps)
         cb._norm_cache = None                          # W changed under torch's feet
         self.last_bmu = bmu
-        loss = (sse / numel).reshape(())
-        if bookkeeping:
-            self._bookkeeping()
         return loss
 
     def checkpoint_dict(self, image_channel):

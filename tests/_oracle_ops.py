@@ -85,6 +85,31 @@ def accumulate(x, geom, bmu_idx, table, num_units, want_counts=False, want_sse=F
     return rbar, counts, sse
 
 
+def accumulate_packed(x, geom, bmu_idx, table, num_units, packed=None, ws=None):
+    d = dim_of(geom)
+    if packed is None:
+        packed = torch.empty(num_units * d + 4, dtype=torch.float32)
+    rbar, _, sse = accumulate(x, geom, bmu_idx, table, num_units, want_sse=True)
+    packed[:num_units * d] = rbar.reshape(-1)
+    hi = sse.to(torch.float32)
+    n = n_patches_of(geom)
+    packed[num_units * d:] = torch.tensor([float(hi), float((sse - hi.double()).to(torch.float32)),
+                                           float(n >> 12), float(n & 4095)])
+    return packed
+
+
+def adam_step_dp(weight, m, v, grad, dim, lr, steps_done, tail, loss_out=None, betas=(0.5, 0.999), eps=1e-8):
+    numel = (float(tail[2]) * 4096.0 + float(tail[3])) * dim
+    step = int(steps_done) + 1
+    adam_step(weight, m, v, grad * torch.tensor(2.0 / numel, dtype=torch.float32), lr, step, betas, eps)
+    steps_done += 1
+    loss = ((tail[0].double() + tail[1].double()) / numel).reshape(1)
+    if loss_out is not None:
+        loss_out.copy_(loss)
+        return loss_out
+    return loss
+
+
 def quantize(idx, table, geom, out=None):
     n, c, h, w, p_h, p_w = geom
     q = table[idx].reshape(n, -1, table.shape[1])

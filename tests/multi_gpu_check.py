@@ -39,10 +39,19 @@ def main():
     dp.broadcast_weights(0)
     ref_cb = make_cb(w0, pd, dev)
     ref = somcb.SomTrainer(ref_cb, lr=1e-4, neighbourhood_step=3)
+    dp_g_cb = make_cb(w0, pd, dev)                          # the same steps through the captured CUDA graph
+    dp_g = somcb.DataParallelSom(dp_g_cb, lr=1e-4, neighbourhood_step=3, use_cuda_graph=True)
     for step in range(6):
-        x = synthetic_fmaps(batch, 500 + step).to(dev)
+        # steps 4 and 5 use a batch that does not divide by the world size (ragged shares)
+        n_f = batch if step < 4 else batch + 1 + step
+        x = synthetic_fmaps(n_f, 500 + step).to(dev)
         l_dp = dp.step(somcb.split_batch(x, world, rank).contiguous())
+        l_g = dp_g.step(somcb.split_batch(x, world, rank).contiguous())
         l_ref = ref.step(x)
+        same_g = torch.equal(dp_g_cb.codebook.weight.data, dp_cb.codebook.weight.data) and float(l_g) == float(l_dp)
+        if rank == 0 and not same_g:
+            print(f"[dp] step {step}: graph-replayed DP step differs from the eager DP step")
+        ok &= same_g
         rel_l = abs(float(l_dp) - float(l_ref)) / abs(float(l_ref))
         rel_w = float((dp_cb.codebook.weight - ref_cb.codebook.weight).norm() / ref_cb.codebook.weight.norm())
         gathered = [torch.empty_like(dp_cb.codebook.weight.data) for _ in range(world)]

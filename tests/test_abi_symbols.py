@@ -34,7 +34,8 @@ def test_binding_table_matches_header():
     from somcb import _lib
     assert sorted(_lib.SIGNATURES) == _declared()
     lib = _lib.load()
-    assert lib.som_version() == 1
+    from somcb import SOM_ABI_VERSION
+    assert lib.som_version() == SOM_ABI_VERSION == 2
     assert lib.som_last_error() is not None
 
 

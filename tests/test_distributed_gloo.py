@@ -81,6 +81,36 @@ def test_data_parallel_matches_single_process(tmp_path):
     assert_close_norm(r0["loss"], losses, 1e-6, "dp loss vs single")
 
 
+def _dp_ragged_body(rank, world, out_dir):
+    """7 feature maps over 2 ranks (4 + 3), then a step where rank 1's share is EMPTY (1 fmap over 2 ranks)."""
+    import somcb
+    import _oracle_ops
+    from _helpers import load_case
+    rec = load_case("c1_trained")
+    cb = _make_cb(rec)
+    tr = somcb.DataParallelSom(cb, lr=1e-4, neighbourhood_step=10 ** 9, ops=_oracle_ops)
+    losses = [tr.step(somcb.split_batch(rec["x"][:7], world, rank).contiguous()),
+              tr.step(somcb.split_batch(rec["x"][7:8], world, rank).contiguous())]
+    torch.save({"w": cb.codebook.weight.detach().clone(), "loss": torch.stack(losses)},
+               os.path.join(out_dir, f"dpr_{rank}.pt"))
+
+
+def test_data_parallel_ragged_and_empty_shares(tmp_path):
+    import somcb
+    import _oracle_ops
+    from _helpers import assert_close_norm, load_case
+    _run("_dp_ragged_body", tmp_path)
+    r0 = torch.load(tmp_path / "dpr_0.pt")
+    r1 = torch.load(tmp_path / "dpr_1.pt")
+    assert torch.equal(r0["w"], r1["w"]) and torch.equal(r0["loss"], r1["loss"])
+    rec = load_case("c1_trained")
+    cb = _make_cb(rec)
+    tr = somcb.SomTrainer(cb, lr=1e-4, neighbourhood_step=10 ** 9, ops=_oracle_ops)
+    losses = torch.stack([tr.step(rec["x"][:7].contiguous()), tr.step(rec["x"][7:8].contiguous())])
+    assert_close_norm(r0["w"], cb.codebook.weight.detach(), 1e-6, "ragged dp weights vs single")
+    assert_close_norm(r0["loss"], losses, 1e-6, "ragged dp loss vs single")
+
+
 def _shard_body(rank, world, out_dir):
     import somcb
     import _oracle_ops

@@ -13,11 +13,19 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+def _f16_ok(d, k):
+    """Shapes an FP16-split kernel covers (include/somcb.h, SOM_BMU_TC_F16)."""
+    return d <= 16 or (d <= 256 and (k + 255) // 256 >= 3)
+
+
 def _variants(n_patches, d, k):
+    """FFMA, the tensor-core variant with its static split rule, and both split arithmetics forced."""
     v = [ops.SOM_BMU_FFMA]
     lib = somcb._lib.load()
     if lib.som_bmu_workspace_bytes(n_patches, d, k, ops.SOM_BMU_TC3X) > 0:
-        v.append(ops.SOM_BMU_TC3X)
+        v += [ops.SOM_BMU_TC3X, ops.SOM_BMU_TC_TF32]
+        if _f16_ok(d, k):
+            v.append(ops.SOM_BMU_TC_F16)
     return v
 
 
@@ -145,12 +153,18 @@ def test_bmu_full_size_c2_properties():
     # permutation invariance: shuffling the fmaps permutes the indices the same way
     perm = torch.randperm(4096, device=DEV)
     assert torch.equal(cb.get_patches_bmu(x[:4096][perm].contiguous(), reshape=True), idx[:4096][perm])
-    sub = x[-256:].cpu()                                  # 65 536 patches incl. the ragged tail
+    # four strided 65 536-patch windows (the last one holds the ragged tail) against the oracle, in the rule's FP16
+    # split and, on the same windows, in 3xTF32
     oc = make_oracle_codebook(w, pd, (32, 32), 4, k // 2)
-    with torch.no_grad():
-        ref = oc.get_patches_bmu(sub)
-    n_bad = assert_bmu_parity(idx[-256:].reshape(-1), ref, flat_patches(sub, pd), w)
-    assert n_bad <= 4
+    cb32 = _gpu_cb(w, pd, (32, 32), 4, k // 2, ops.SOM_BMU_TC_TF32)
+    for lo in (0, 13000, 26000, n_f - 256):
+        sub = x[lo:lo + 256].cpu()
+        with torch.no_grad():
+            ref = oc.get_patches_bmu(sub)
+        n_bad = assert_bmu_parity(idx[lo:lo + 256].reshape(-1), ref, flat_patches(sub, pd), w)
+        assert n_bad <= 4
+        n_bad = assert_bmu_parity(cb32.get_patches_bmu(x[lo:lo + 256].contiguous()), ref, flat_patches(sub, pd), w)
+        assert n_bad <= 4
 
 
 @pytest.mark.parametrize("geom", [
@@ -198,22 +212,22 @@ def test_tensor_core_ties_inside_and_across_chunks():
         assert_bmu_parity(idx, ref, flat_patches(x, pd), w)
 
 
-@pytest.mark.parametrize("env", [{"SOM_TC_PAIR": "1"}, {"SOM_TC_PAIR": "0"}])
-def test_alternate_tensor_core_paths_in_a_subprocess(env):
-    """The static dispatch uses CTA pairs (cta_group::2) only for problems of at least two waves of patch
-    tiles.  The override switch is read once per process, so the forced-pair and forced-single variants run
-    the parity probe in their own interpreter on small shapes of every mode (resident-A, streamed, split-K)."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    probe = os.path.join(root, "tests", "tc_probe.py")
-    shapes = [("16", "8", "2048"), ("40", "4", "1000"), ("3", "8", "777"), ("64", "32", "512"), ("700", "4", "600")]
-    for shp in shapes:
-        r = subprocess.run([sys.executable, probe, *shp, "2"], env={**os.environ, **env},
-                           capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, f"{env} {shp}: {r.stdout[-400:]} {r.stderr[-800:]}"
-        assert "OK:" in r.stdout, r.stdout[-400:]
+@pytest.mark.parametrize("variant", [ops.SOM_BMU_TC_TF32, ops.SOM_BMU_TC_F16])
+@pytest.mark.parametrize("fmaps,p,k", [(640, 4, 2048), (2400, 8, 1024), (1200, 8, 3000)])
+def test_cta_pair_paths_of_both_arithmetics(variant, fmaps, p, k):
+    """The static dispatch uses CTA pairs (cta_group::2) from two waves of 128-patch tiles on (296 tiles on a
+    148-SM part): 40 960 patches of D = 64 and 38 400 / 19 200 of D = 256 (the last one: one wave, unpaired 3xTF32,
+    FP16 not selected by the rule but forced) -- each arithmetic against the live oracle."""
+    pd = (p, p)
+    x = synthetic_fmaps(fmaps, 91)
+    w = trained_like_codebook(k, pd, 13)
+    oc = make_oracle_codebook(w, pd, (32, 32), 4, k // 2)
+    with torch.no_grad():
+        ref = oc.get_patches_bmu(x)
+    cb = _gpu_cb(w, pd, (32, 32), 4, k // 2, variant)
+    idx = cb.get_patches_bmu(x.to(DEV)).cpu()
+    n_bad = assert_bmu_parity(idx, ref, flat_patches(x, pd), w)
+    assert n_bad == 0, f"{n_bad} index mismatches on a trained-like codebook (variant {variant})"
 
 
 @pytest.mark.parametrize("pd,fmaps", [((4, 4), 64), ((8, 8), 16)])
@@ -303,24 +317,100 @@ def test_non_finite_patches_take_unit_zero_and_leave_their_neighbours_alone(fmap
         assert float(same.float().mean()) > 0.999
 
 
-@pytest.mark.parametrize("mode", ["1", "0"])
-def test_config_s_split_modes_in_a_subprocess(mode):
-    """The config-S kernel (D <= 16) has two operand splits: FP16 (kind::f16, 4 MMAs per tile, per-patch and
-    per-codebook power-of-two scaling) and TF32 (7 MMAs per tile).  SOM_TC_S_F16 is read once per process, so each
-    mode runs the parity probe in its own interpreter: trained-like and fresh codebooks, ragged D, and data / codebook
-    magnitudes from 1e-6 to 1e4 (outside FP16's range without the scaling)."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    probe = os.path.join(root, "tests", "tc_probe.py")
-    runs = [(("64", "2", "4096", "2"), "1"), (("64", "2", "4096", "2", "fresh"), "1"), (("48", "2", "777", "2"), "1"),
-            (("64", "2", "4096", "2"), "1e-6"), (("64", "2", "4096", "2"), "1e-3"), (("64", "2", "4096", "2"), "1e4"),
-            (("64", "1", "300", "2"), "1"), (("40", "2", "20000", "2"), "1")]
-    for shp, scale in runs:
-        r = subprocess.run([sys.executable, probe, *shp], capture_output=True, text=True, timeout=300,
-                           env={**os.environ, "SOM_TC_S_F16": mode, "SOM_PROBE_SCALE": scale})
-        assert r.returncode == 0, f"mode {mode} {shp} x{scale}: {r.stdout[-400:]} {r.stderr[-800:]}"
-        assert "OK:" in r.stdout, r.stdout[-400:]
-        if scale == "1" and "fresh" not in shp:
-            assert "OK: 0 near-tie diffs" in r.stdout, r.stdout[-300:]
+@pytest.mark.parametrize("variant", [ops.SOM_BMU_TC_F16, ops.SOM_BMU_TC_TF32])
+def test_split_arithmetics_over_magnitudes(variant):
+    """Both operand splits of the tensor-core kernels -- FP16 (kind::f16, per-patch and per-codebook power-of-two
+    scaling) and TF32 -- on config S (D <= 16), D = 64 and D = 256: trained-like and fresh codebooks, ragged D, and
+    data / codebook magnitudes from 1e-6 to 1e4 (outside FP16's range without the scaling)."""
+    runs = [((64, 2, 4096), 1.0, False), ((64, 2, 4096), 1.0, True), ((48, 2, 777), 1.0, False),
+            ((64, 2, 4096), 1e-6, False), ((64, 2, 4096), 1e-3, False), ((64, 2, 4096), 1e4, False),
+            ((64, 1, 300), 1.0, False), ((40, 2, 20000), 1.0, False),
+            ((320, 4, 2048), 1.0, False), ((320, 4, 2048), 1.0, True), ((320, 4, 2048), 1e-6, False),
+            ((320, 4, 2048), 1e-3, False), ((320, 4, 2048), 1e4, False), ((64, 4, 1000), 1.0, False),
+            ((160, 8, 1024), 1.0, False), ((160, 8, 1024), 1e-6, False), ((160, 8, 1024), 1e4, False),
+            ((160, 8, 1024), 1.0, True)]
+    for (fmaps, p, k), scale, fresh in runs:
+        pd = (p, p)
+        d = 4 * p * p
+        x = synthetic_fmaps(fmaps, 4242)
+        if fresh:
+            w = torch.empty(k, d).uniform_(-1 / k, 1 / k, generator=torch.Generator().manual_seed(0))
+        else:
+            w = trained_like_codebook(k, pd, 7)
+        x, w = x * scale, w * scale
+        oc = make_oracle_codebook(w, pd, (32, 32), 4, k // 2)
+        with torch.no_grad():
+            ref = oc.get_patches_bmu(x)
+        cb = _gpu_cb(w, pd, (32, 32), 4, k // 2, variant)
+        idx = cb.get_patches_bmu(x.to(DEV)).cpu()
+        n_bad = assert_bmu_parity(idx, ref, flat_patches(x, pd), w)
+        if scale == 1.0 and not fresh:
+            assert n_bad == 0, f"variant {variant} {fmaps, p, k}: {n_bad} near-tie diffs on a trained-like codebook"
+
+
+def test_mixed_row_magnitudes_fp16_split():
+    """Patch rows of wildly different magnitude inside ONE 128-row tile (each row carries its own power-of-two
+    scale) and an all-zero row, FP16 split at D = 64 and D = 16, against the fp64 argmin."""
+    from oracle import bmu_fp64
+    for p, k in ((4, 2048), (2, 4096)):
+        pd = (p, p)
+        x = synthetic_fmaps(64, 7)
+        mags = 10.0 ** torch.randint(-6, 5, (64, 1, 32 // p, 1, 32 // p, 1),
+                                     generator=torch.Generator().manual_seed(3)).float()
+        x = (x.reshape(64, 4, 32 // p, p, 32 // p, p) * mags).reshape(64, 4, 32, 32).contiguous()
+        x[5] = 0.0
+        w = trained_like_codebook(k, pd, 7)
+        flat = flat_patches(x, pd)
+        ref = bmu_fp64(flat, w)
+        cb = _gpu_cb(w, pd, (32, 32), 4, k // 2, ops.SOM_BMU_TC_F16)
+        idx = cb.get_patches_bmu(x.to(DEV)).cpu()
+        assert_bmu_parity(idx, ref, flat, w)
+
+
+def test_c4_shape_parity_65536_patches_both_arithmetics():
+    """BASELINE config 4's shape (D = 64, K = 16 384) on 65 536 patches -- 512 patch tiles, the CTA-pair path -- against
+    the chunked live oracle, for the rule's choice (FP16 split) and for 3xTF32."""
+    pd, k = (4, 4), 16384
+    x = synthetic_fmaps(1024, 314)
+    w = trained_like_codebook(k, pd, 7)
+    oc = make_oracle_codebook(w, pd, (32, 32), 4, k // 2)
+    with torch.no_grad():
+        ref = torch.cat([oc.get_patches_bmu(x[i:i + 128]) for i in range(0, 1024, 128)])
+    flat = flat_patches(x, pd)
+    assert somcb._lib.load().som_bmu_split_mode(65536, 64, k) == 1
+    for variant in (ops.SOM_BMU_AUTO, ops.SOM_BMU_TC_TF32):
+        cb = _gpu_cb(w, pd, (32, 32), 4, k // 2, variant)
+        idx = cb.get_patches_bmu(x.to(DEV)).cpu()
+        n_bad = assert_bmu_parity(idx, ref, flat, w)
+        assert n_bad <= 2, f"variant {variant}: {n_bad} near-tie differences"
+
+
+def test_c5_full_codebook_262144_units():
+    """BASELINE config 5 with ALL 262 144 units (D = 256, 268 MB of codebook) on one GPU: 1024 patches against the live
+    oracle, 38 400 patches (FP16 split, CTA pairs) against the eight-shard search merged with som_merge_candidates."""
+    pd, k = (8, 8), 262144
+    gw = torch.Generator().manual_seed(77)
+    w = torch.tanh(torch.randn(k, 256, generator=gw))
+    x = synthetic_fmaps(2400, 2718)
+    oc = make_oracle_codebook(w, pd, (32, 32), 4, k // 2)
+    with torch.no_grad():
+        ref = oc.get_patches_bmu(x[:64])
+    wd, xd = w.to(DEV), x.to(DEV)
+    geom_s = ops.geometry(x[:64].shape, pd)
+    small = ops.bmu(xd[:64].contiguous(), geom_s, wd).cpu()
+    assert_bmu_parity(small, ref, flat_patches(x[:64], pd), w)
+    geom = ops.geometry(x.shape, pd)
+    full = ops.bmu(xd, geom, wd)
+    assert_bmu_parity(full[:1024].cpu(), ref, flat_patches(x[:64], pd), w)
+    rds, idxs = [], []
+    for r in range(8):
+        lo, hi = somcb.shard_bounds(k, 8, r)
+        i, rd = ops.bmu(xd, geom, wd[lo:hi].contiguous(), unit_offset=lo, want_rd=True)
+        rds.append(rd)
+        idxs.append(i)
+    merged, _ = ops.merge_candidates(torch.stack(rds), torch.stack(idxs))
+    diff = torch.nonzero(merged != full).flatten().cpu()
+    if diff.numel():          # shards carry their own codebook scale: near-ties may resolve differently
+        flat = flat_patches(x, pd)[diff]
+        assert_bmu_parity(merged.cpu()[diff], full.cpu()[diff], flat, w)
+    assert diff.numel() <= 4

@@ -440,3 +440,22 @@ def test_empty_batch_is_a_no_op_with_the_reference_shapes():
     rc = lib.som_bmu_nchw_f32(None, 1, 4, 32, 32, 4, 4, cb.codebook.weight.data_ptr(), cn.data_ptr(), 256, 0,
                               None, None, None, 0, ops.SOM_BMU_AUTO, st)
     assert rc == -1 and b"null pointer" in lib.som_last_error()
+
+
+def test_multi_gpu_paths_under_torchrun():
+    """With at least two GPUs visible: tests/multi_gpu_check.py under torch.distributed.run over NCCL -- data-parallel
+    trainer (eager and CUDA-graph, ragged shares) == one-GPU trainer with bit-identical replicas, unit-sharded search ==
+    unsharded search, sharded histogram.  Skips on a one-GPU box (the gloo tests cover the host logic on CPU)."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731",
+                        os.path.join(root, "tests", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -95,8 +95,9 @@ def test_shard_arithmetic():
         assert max(sizes) - min(sizes) <= 1
     x = torch.arange(8).reshape(8, 1, 1, 1)
     assert somcb.split_batch(x, 4, 2).flatten().tolist() == [4, 5]
-    with pytest.raises(ValueError):
-        somcb.split_batch(x, 3, 0)
+    # ragged (and empty) shares are allowed: the step all-reduces the patch count
+    assert [somcb.split_batch(x, 3, r).shape[0] for r in range(3)] == [3, 3, 2]
+    assert [somcb.split_batch(x[:2], 4, r).shape[0] for r in range(4)] == [1, 1, 0, 0]
 
 
 @pytest.mark.parametrize("name", CASES)
