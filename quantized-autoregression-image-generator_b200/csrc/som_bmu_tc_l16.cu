@@ -515,7 +515,8 @@ static bool make_plan(Plan* pl, int64_t n, int D, int K, bool force) {
     if (force && pl->DB > 2 && pl->n_mtiles >= 2 && sms % 2 == 0) pl->cg = 2;
     pl->NA = pl->DB <= 2 ? 2 : 4;
     // four-slot tiles leave 64 KB for the B ring: only CTA pairs (16 KB half blocks) keep enough stages in flight
-    if (pl->NA == 4 && pl->cg != 2) return false;
+    // (a forced single-CTA launch runs with two 32 KB stages: correct, not fast)
+    if (pl->NA == 4 && pl->cg != 2 && !force) return false;
     pl->NB = (RING_BYTES - pl->NA * A_SLOT_BYTES) / (B_BLK_BYTES / pl->cg);
     if (pl->NB > NB_MAX) pl->NB = NB_MAX;
     size_t o = 0;

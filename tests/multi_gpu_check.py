@@ -83,9 +83,14 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("MULTI_GPU_CHECK", "PASS" if int(flag) else "FAIL")
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag) else 1)
+        print("MULTI_GPU_CHECK", "PASS" if int(flag) else "FAIL", flush=True)
+    # captured CUDA graphs hold NCCL kernels and destroy_process_group() can block behind them: release the graphs
+    # and leave without tearing the communicator down
+    dp_g._graphs.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0 if int(flag) else 1)
 
 
 if __name__ == "__main__":
