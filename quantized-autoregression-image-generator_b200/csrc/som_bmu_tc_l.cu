@@ -505,7 +505,7 @@ bmu_tc_l_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
-                            if (CG == 2) mbar_arrive_remote(&bars.acc_empty[acc], 0);
+                            if (CG == 2) mbar_arrive_remote_relaxed(&bars.acc_empty[acc], 0);
                             else mbar_arrive(&bars.acc_empty[acc]);
                         }
                     }

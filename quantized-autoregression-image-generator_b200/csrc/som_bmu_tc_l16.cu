@@ -97,19 +97,28 @@ __device__ __forceinline__ uint4 pack_h8(float v0, float v1, float v2, float v3,
                       *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
 }
 
-template <int CG>
+__device__ long long g_prof16[8];             // CTA 0's MMA loop: cycles, tiles, cycles waiting (acc_empty, B, A)
+
+// MERGED (D <= 128): one ring stage carries everything a unit tile needs of one 64-feature block -- B_hi, B_lo and
+// (block 0) the norm tail -- so the issuing thread pays ONE barrier wait and ONE commit per block instead of three.
+// With 13 MMAs per tile the issuing thread, not the tensor pipe, sets the pace otherwise (~48 cycles per MMA issue,
+// ~100 per barrier check, ~120 per commit).
+template <int CG, bool MERGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int B_STAGE = B_BLK_BYTES / CG;       // this CTA's share of a 256-unit block
     constexpr int T_STAGE = TAIL_B_BYTES / CG;
+    constexpr int M_STAGE = 2 * B_STAGE + T_STAGE;  // merged stage: [hi | lo | tail]
     const int NA = P.NA, NB = P.NB, DB = P.DB;
+    // separate rings : [A slots | B stages ........ | A tails | B tail stages]
+    // merged stages  : [A slots (2) | A tails | merged stages ....................]
     uint8_t* a_ring = tiles;
-    uint8_t* b_ring = a_ring + (size_t)NA * A_SLOT_BYTES;
-    uint8_t* a_tail = tiles + RING_BYTES;
-    uint8_t* t_ring = a_tail + 2 * TAIL_A_BYTES;
-    Aux& aux = *reinterpret_cast<Aux*>(t_ring + 2 * TAIL_B_BYTES);
+    uint8_t* a_tail = MERGED ? tiles + 2 * A_SLOT_BYTES : tiles + RING_BYTES;
+    uint8_t* b_ring = MERGED ? a_tail + 2 * TAIL_A_BYTES : a_ring + (size_t)NA * A_SLOT_BYTES;
+    uint8_t* t_ring = a_tail + 2 * TAIL_A_BYTES;    // (separate rings only)
+    Aux& aux = *reinterpret_cast<Aux*>(tiles + TILES_BYTES);
     Barriers& bars = aux.bars;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
     const int job0 = (CG == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
@@ -162,6 +171,24 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
             const int row_off = (int)rank * (TN / CG);
             for (int q = job0; q < n_jobs; q += job_stride) {
                 for (int n = 0; n < P.NT; ++n) {
+                    if (MERGED) {
+                        for (int fb = 0; fb < DB; ++fb) {
+                            mbar_wait(&bars.b_empty[bs], b_ph ^ 1);
+                            if (rank == 0) mbar_expect_tx(&bars.b_full[bs], 2 * B_BLK_BYTES + (fb == 0 ? TAIL_B_BYTES : 0));
+                            uint8_t* dst = b_ring + (size_t)bs * M_STAGE;
+#pragma unroll
+                            for (int part = 0; part < 2; ++part) {
+                                if (CG == 1) tma_load_2d(&map_b, &bars.b_full[bs], dst + part * B_STAGE, (part * DB + fb) * KBLK, n * TN);
+                                else tma_load_2d_pair(&map_b, &bars.b_full[bs], dst + part * B_STAGE, (part * DB + fb) * KBLK, n * TN + row_off);
+                            }
+                            if (fb == 0) {
+                                if (CG == 1) tma_load_2d(&map_t, &bars.b_full[bs], dst + 2 * B_STAGE, 0, n * TN);
+                                else tma_load_2d_pair(&map_t, &bars.b_full[bs], dst + 2 * B_STAGE, 0, n * TN + row_off);
+                            }
+                            if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                        }
+                        continue;
+                    }
                     mbar_wait(&bars.t_empty[ts], t_ph ^ 1);
                     if (rank == 0) mbar_expect_tx(&bars.t_full[ts], TAIL_B_BYTES);
                     if (CG == 1) tma_load_2d(&map_t, &bars.t_full[ts], t_ring + ts * T_STAGE, 0, n * TN);
@@ -198,13 +225,59 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
         constexpr uint32_t B_UNITS = (uint32_t)B_STAGE >> 4;
         constexpr uint32_t T_UNITS = (uint32_t)T_STAGE >> 4;
         constexpr uint32_t TA_UNITS = (uint32_t)TAIL_A_BYTES >> 4;
+        constexpr uint32_t M_UNITS = (uint32_t)M_STAGE >> 4;
         int bs = 0, ts = 0;
         uint32_t b_ph = 0, t_ph = 0, j = 0;
         int i = 0;
+        const bool prof = blockIdx.x == 0;
+        long long w_acc = 0, w_b = 0, w_a = 0;
+        const long long t_begin = clock64();
         for (int q = job0; q < n_jobs; q += job_stride, ++i) {
             for (int n = 0; n < P.NT; ++n) {
+                long long c0 = prof ? clock64() : 0;
                 mma_wait(&bars.acc_empty[j & 1u], ((j >> 1) & 1u) ^ 1u);
+                if (prof) w_acc += clock64() - c0;
                 const uint32_t d_addr = tmem_base + (j & 1u) * TN;
+                if (MERGED) {
+                    for (int fb = 0; fb < DB; ++fb) {
+                        const int nks = (fb == DB - 1) ? P.nks_last : 4;
+                        const int u = i * DB + fb;
+                        const int as = u % NA;
+                        if (n == 0) {
+                            c0 = prof ? clock64() : 0;
+                            mma_wait(&bars.a_full[as], (uint32_t)(u / NA) & 1u);
+                            if (prof) w_a += clock64() - c0;
+                        }
+                        const uint64_t ahi = adesc0 + (uint32_t)as * A_SLOT_UNITS;
+                        const uint64_t alo = ahi + A_LO_UNITS;
+                        c0 = prof ? clock64() : 0;
+                        mma_wait(&bars.b_full[bs], b_ph);
+                        if (prof) w_b += clock64() - c0;
+                        tc_fence_after();
+                        const uint64_t bhi = bdesc0 + (uint32_t)bs * M_UNITS;
+                        const uint64_t blo = bhi + B_UNITS;
+                        if (leader) {
+                            if (fb == 0)
+                                tc_mma_f16_cg<CG>(d_addr, atdesc0 + (uint32_t)(i & 1) * TA_UNITS,
+                                                  umma_desc_sw32(smem_u32(b_ring + (size_t)bs * M_STAGE + 2 * B_STAGE)), 0u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < nks) tc_mma_f16_cg<CG>(d_addr, ahi + 2u * k, bhi + 2u * k, 1u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < nks) tc_mma_f16_cg<CG>(d_addr, alo + 2u * k, bhi + 2u * k, 1u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < nks) tc_mma_f16_cg<CG>(d_addr, ahi + 2u * k, blo + 2u * k, 1u);
+                            tc_commit_cg<CG>(&bars.b_empty[bs]);
+                            if (n == P.NT - 1) tc_commit_cg<CG>(&bars.a_empty[as]);
+                        }
+                        if (++bs == NB) { bs = 0; b_ph ^= 1; }
+                    }
+                    if (leader) tc_commit_cg<CG>(&bars.acc_full[j & 1u]);
+                    ++j;
+                    continue;
+                }
                 mma_wait(&bars.t_full[ts], t_ph);
                 if (n == 0) {                   // block 0 of this job (and with it the job's tail rows)
                     const int u = i * DB;
@@ -251,6 +324,10 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
                 if (leader) tc_commit_cg<CG>(&bars.acc_full[j & 1u]);
                 ++j;
             }
+        }
+        if (prof && leader && j > 0) {
+            g_prof16[0] = clock64() - t_begin; g_prof16[1] = (long long)j;
+            g_prof16[2] = w_acc; g_prof16[3] = w_b; g_prof16[4] = w_a;
         }
     } else if (warp >= BUILD_WARP0 && warp < BUILD_WARP0 + BUILD_WARPS) {
         // ================================ A builders ==================================
@@ -397,7 +474,7 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (CG == 2) mbar_arrive_remote(&bars.acc_empty[acc], 0);
+                    if (CG == 2) mbar_arrive_remote_relaxed(&bars.acc_empty[acc], 0);
                     else mbar_arrive(&bars.acc_empty[acc]);
                 }
                 consume(vb, 3);
@@ -494,7 +571,7 @@ __global__ void __launch_bounds__(256) split_w_l16_kernel(const float* __restric
 }
 
 struct Plan {
-    int cg, D, K, DB, nks_last, K_pad, NT, n_mtiles, NA, NB;
+    int cg, merged, D, K, DB, nks_last, K_pad, NT, n_mtiles, NA, NB;
     size_t off_b, off_t, off_s, total;
 };
 
@@ -517,7 +594,9 @@ static bool make_plan(Plan* pl, int64_t n, int D, int K, bool force) {
     // four-slot tiles leave 64 KB for the B ring: only CTA pairs (16 KB half blocks) keep enough stages in flight
     // (a forced single-CTA launch runs with two 32 KB stages: correct, not fast)
     if (pl->NA == 4 && pl->cg != 2 && !force) return false;
-    pl->NB = (RING_BYTES - pl->NA * A_SLOT_BYTES) / (B_BLK_BYTES / pl->cg);
+    pl->merged = pl->NA == 2 ? 1 : 0;
+    if (pl->merged) pl->NB = (TILES_BYTES - 2 * A_SLOT_BYTES - 2 * TAIL_A_BYTES) / ((2 * B_BLK_BYTES + TAIL_B_BYTES) / pl->cg);
+    else pl->NB = (RING_BYTES - pl->NA * A_SLOT_BYTES) / (B_BLK_BYTES / pl->cg);
     if (pl->NB > NB_MAX) pl->NB = NB_MAX;
     size_t o = 0;
     pl->off_b = o; o = align_up(o + (size_t)pl->K_pad * pl->DB * 64 * 2 * 2, 1024);
@@ -577,10 +656,11 @@ int launch_bmu_tc_l16(const float* x, const Geom& g, const float* W, const float
     P.x = x; P.g = g; P.scale = scale;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
-    static const KernelFn kernels[2] = {bmu_tc_l16_kernel<1>, bmu_tc_l16_kernel<2>};
+    static const KernelFn kernels[4] = {bmu_tc_l16_kernel<1, false>, bmu_tc_l16_kernel<2, false>,
+                                        bmu_tc_l16_kernel<1, true>, bmu_tc_l16_kernel<2, true>};
     static PerDeviceFlag attr_done;
     if (attr_done.pending()) {
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 4; ++c) {
             cudaError_t e = cudaFuncSetAttribute(kernels[c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
             if (e != cudaSuccess) { set_error("bmu(tc f16): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
         }
@@ -601,9 +681,15 @@ int launch_bmu_tc_l16(const float* x, const Geom& g, const float* W, const float
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kernels[pl.cg - 1], map_b, map_t, P);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kernels[2 * pl.merged + pl.cg - 1], map_b, map_t, P);
     if (le != cudaSuccess) { set_error("bmu_tc_l16_kernel: launch: %s", cudaGetErrorString(le)); return (int)le; }
     return check_launch("bmu_tc_l16_kernel");
 }
 
 }  // namespace som
+
+// debug: CTA 0's MMA issue loop in the last FP16-split launch: cycles, tiles, cycles waiting for a free accumulator
+// (epilogue), for B stages (TMA) and for A tiles (builders)
+extern "C" SOM_API int som_debug_tc_l16_cycles(long long* out5) {
+    return (int)cudaMemcpyFromSymbol(out5, som::tcl16::g_prof16, 5 * sizeof(long long));
+}

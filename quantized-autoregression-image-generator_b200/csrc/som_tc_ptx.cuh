@@ -114,6 +114,19 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
         "}\n" ::"r"(smem_u32(bar)), "r"(cta)
         : "memory");
 }
+// The same arrival WITHOUT release semantics: for signals that publish no memory writes (an epilogue warp handing a
+// TMEM accumulator back after tcgen05.ld + tcgen05.fence::before_thread_sync).  The release form compiles to
+// MEMBAR.ALL.GPU + ERRBAR in front of the arrive (ncu: 16 % of all stall samples of the FP16-split kernel, on the
+// critical path of every tile).
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
 // bounded wait with cluster-scope acquire (barriers that peer CTAs arrive on)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
