@@ -230,10 +230,10 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # headline: the C4 step, strong-scaled
 # ---------------------------------------------------------------------------------------------------------------
-def _make_trainer(cb, world, graph=True):
+def _make_trainer(cb, world, graph=True, tail="auto"):
     import somcb
     kw = dict(lr=C4["lr"], neighbourhood_step=C4["neighbourhood_step"], use_cuda_graph="alias" if graph else False)
-    return somcb.DataParallelSom(cb, **kw) if world > 1 else somcb.SomTrainer(cb, **kw)
+    return somcb.DataParallelSom(cb, tail=tail, **kw) if world > 1 else somcb.SomTrainer(cb, **kw)
 
 
 def run_headline(args, dev, world, rank, peaks):
@@ -249,9 +249,11 @@ def run_headline(args, dev, world, rank, peaks):
     # global batch b = fmaps of seed 5000 + b (generated per rank for its own contiguous share: seeds differ per rank)
     xs = [_fmaps(share, 5000 + 131 * b + rank, dev) for b in range(n_rot)]
     cb = _codebook(C4["K"], C4["patch"], dev)
-    tr = _make_trainer(cb, world)
+    tr = _make_trainer(cb, world, tail=args.tail)
     if world > 1:
         tr.broadcast_weights(0)
+    tail_mode = getattr(tr, "tail", "single")
+    _log(f"trainer ready (tail: {tail_mode})")
     # set-up (untimed, before the warm-up): one eager step (kernel attributes, NCCL communicator), then one graph
     # capture per rotation buffer
     l0 = lib.som_launch_count()
@@ -352,9 +354,34 @@ def run_headline(args, dev, world, rank, peaks):
     if world > 1:
         scratch = packed.clone()
         dist.barrier()
-        parts["all_reduce"] = _timed(lambda: dist.all_reduce(scratch), reps)
+        parts["nccl_all_reduce_4MB (reference point)"] = _timed(lambda: dist.all_reduce(scratch), reps)
+    if world > 1 and tail_mode == "peer":
+        # the sharded tail replaces filter_W / filter_Rbar / adam / all_reduce above by their per-slice forms
+        lo_u, hi_u, g0, g1, max_own, max_halo = tr._slices(ops.filter_half_width(k, rng))
+        if 4 * max_halo <= 3 * k and hi_u > lo_u:
+            pm, mc = tr.peer, tr._mc
+            sig, rk = pm.signal_ptrs, pm.rank
+            rsum = torch.empty(g1 - g0, d, dtype=torch.float32, device=dev)
+            tl = torch.empty(4, dtype=torch.float32, device=dev)
+            wth = ops.neighbourhood_filter(w[g0:g1], rng)
+            mm, vv = torch.zeros(hi_u - lo_u, d, device=dev), torch.zeros(hi_u - lo_u, d, device=dev)
+            ops.peer_reduce_rows(mc["packed"], k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1)
+            gh = ops.neighbourhood_filter(rsum, rng)
+            dist.barrier()
+            for name in ("filter_W", "filter_Rbar", "adam"):
+                parts.pop(name)
+            parts["slice: filter_W rows"] = _timed(lambda: ops.neighbourhood_filter(w[g0:g1], rng), reps)
+            parts["slice: multicast W~ rows + barrier"] = _timed(
+                lambda: ops.peer_bcast_rows(wth[lo_u - g0:hi_u - g0], mc["wt"] + lo_u * d * 4, max_own * d, rk, world, sig, 0), reps)
+            parts["slice: in-switch reduce of Rbar rows + halo"] = _timed(
+                lambda: ops.peer_reduce_rows(mc["packed"], k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1), reps)
+            parts["slice: filter_Rbar rows"] = _timed(lambda: ops.neighbourhood_filter(rsum, rng), reps)
+            # (Adam here re-broadcasts the CURRENT rows: lr = 0 keeps the replicas' weights unchanged)
+            parts["slice: adam + multicast W rows + barrier"] = _timed(
+                lambda: ops.peer_adam_slice(w[lo_u:hi_u], mc["w"] + lo_u * d * 4, mm, vv, gh[lo_u - g0:hi_u - g0], max_own * d,
+                                            d, 0.0, tdev, tl, rk, world, sig, 2), reps)
     parts = {kk: _max_over_ranks(v, dev, world) for kk, v in parts.items()}
-    ksum = sum(parts.values())
+    ksum = sum(v for kk, v in parts.items() if "reference point" not in kk)
     breakdown = {kk: {"ms": v, "pct_of_step": 100.0 * v / ms_step} for kk, v in parts.items()}
     breakdown["sum_of_parts_ms"] = ksum
     breakdown["graph_step_ms"] = ms_step
@@ -402,6 +429,7 @@ def run_headline(args, dev, world, rank, peaks):
                         "l2": f"each rank rotates through {n_rot} distinct resident batches "
                               f"({n_rot * share_bytes >> 20} MB > the 126 MB L2), so no step re-reads a batch that is "
                               "still L2 resident",
+                        "dp_tail": tail_mode,
                         "allreduce_bytes_per_step": (k * d + 4) * 4 if world > 1 else 0}}
     return head, tr, cb, xs
 
@@ -561,6 +589,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 20)")
+    ap.add_argument("--tail", default="auto", choices=["auto", "peer", "nccl"],
+                    help="data-parallel tail: sharded over NVSwitch multicast peer memory, or NCCL all-reduce + replicated")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -570,6 +600,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (our arm) needs a CUDA device: somcb has no CPU fallback")
+    # stdout carries ONE JSON line: NCCL writes its version banner to file descriptor 1 whatever NCCL_DEBUG says, so
+    # everything else that lands on fd 1 during the run is sent to stderr and the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import somcb  # noqa: F401
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -628,7 +663,7 @@ def main():
                 "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
                 "roofline": head["roofline"], "breakdown": head["breakdown"], "cpu_baseline": cpu_base,
                 "extra": extra or None}
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # no destroy_process_group(): NCCL's communicator teardown can block behind CUDA-graph-captured collectives
         # (seen on this stack: the process printed its result and then never exited).  The result is out; leave.

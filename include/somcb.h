@@ -126,6 +126,10 @@ SOM_API int som_filter_f32(const float* in, float* out, int K, int D, double nei
  * S @ W (models/Codebook.py:128-130) and its autograd transpose like som_filter_f32.
  * som_filter_workspace_bytes returns 0 when the shape takes the FFMA kernel.                               */
 SOM_API size_t som_filter_workspace_bytes(int K, int D, double neighbourhood_range);
+/* Band half-width h of T for this range: the largest |j - a| whose fp32 weight is non-zero (at most K - 1).  Row a
+ * of the output depends on input rows [a - h, a + h] only, which is what lets a rank filter a slice of units from
+ * the slice plus an h-row halo (host-only, no device work).                                                   */
+SOM_API int    som_filter_half_width(int K, double neighbourhood_range);
 SOM_API int som_filter_ws_f32(const float* in, float* out, int K, int D, double neighbourhood_range,
                       float scale, void* ws, size_t ws_bytes, void* stream);
 
@@ -185,6 +189,39 @@ SOM_API int som_adam_devstep_f32(float* W, float* m, float* v, const float* g, i
 SOM_API int som_adam_dp_f32(float* W, float* m, float* v, const float* g, int64_t n, int D,
                     double lr, double b1, double b2, double eps, int64_t* steps_done,
                     const float* tail, double* loss_out, void* stream);
+
+/* ---- data-parallel tail over NVLink / NVSwitch peer memory (new; multi-GPU only) -------------------------
+ * Replaces, across ranks, "all-reduce the accumulators, then every rank filters and updates the whole codebook"
+ * (train_codebook.py:240-242 + models/Codebook.py:112-130 have no multi-GPU form in the reference).  Pointers
+ * named mc_* are NVSwitch MULTICAST addresses of caller-owned symmetric allocations (the same offset in the same
+ * allocation on every rank); `signal_pads` is a HOST array of `world` device pointers, entry r = rank r's flag
+ * area (som_peer_signal_bytes() bytes, zero-filled once, peer-mapped) as seen from THIS rank.  Every call must be
+ * made by all ranks in the same order with the same `channel` (0..3) and the same max_* arguments (the grids pair
+ * up block by block across ranks); flags reset themselves, so the calls can be replayed from a CUDA graph.
+ * A peer that never arrives makes the kernel trap after ~4 s instead of hanging.                               */
+SOM_API size_t som_peer_signal_bytes(void);
+/* In-place all-reduce(sum) of n floats (n % 4 == 0): rank r reduces quads [r*n/4/world, ...) in the switch
+ * (multimem.ld_reduce) and stores them to every rank (multimem.st).                                          */
+SOM_API int som_peer_allreduce_f32(void* mc_buf, int64_t n, int rank, int world, void* const* signal_pads,
+                           int channel, void* stream);
+/* Rows [row0, row1) of the K x D accumulator matrix at mc_packed (layout of som_accumulate_packed_nchw_f32),
+ * reduced over the ranks into LOCAL out_rows, and the reduced 4-float tail into LOCAL out_tail: the
+ * reduce-scatter half of the all-reduce for a rank that owns a slice of units plus the filter's halo.
+ * max_rows = the largest row1 - row0 of any rank.  Waits until every rank's accumulators are complete.       */
+SOM_API int som_peer_reduce_rows_f32(const void* mc_packed, int K, int D, int row0, int row1, int max_rows,
+                             float* out_rows, float* out_tail, int rank, int world,
+                             void* const* signal_pads, int channel, void* stream);
+/* n floats of local src_rows stored to mc_dst_rows on every rank, then a barrier over the ranks: when the call
+ * has completed on a rank, every rank's rows have landed in its copy.  max_n = the largest n of any rank.      */
+SOM_API int som_peer_bcast_rows_f32(const float* src_rows, void* mc_dst_rows, int64_t n, int64_t max_n, int rank,
+                            int world, void* const* signal_pads, int channel, void* stream);
+/* som_adam_dp_f32 on the n weights of this rank's rows (all pointers address the slice; W_rows is this rank's
+ * local copy, read) with the updated rows stored to mc_W_rows on EVERY rank -- the all-gather fused into the
+ * update -- then the barrier over the ranks.                                                                 */
+SOM_API int som_peer_adam_slice_f32(const float* W_rows, void* mc_W_rows, float* m_rows, float* v_rows,
+                            const float* g_rows, int64_t n, int64_t max_n, int D, double lr, double b1,
+                            double b2, double eps, int64_t* steps_done, const float* tail, double* loss_out,
+                            int rank, int world, void* const* signal_pads, int channel, void* stream);
 
 /* ---- row compaction for pruning ----------------------------------------------------------
  * out[r] = W[keep[r]] for r < n_keep (prune_codebook.py:161-162).                        */

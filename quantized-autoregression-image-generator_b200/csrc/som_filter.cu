@@ -242,6 +242,11 @@ static inline float two_var_of(double neighbourhood_range) {
 
 using namespace som;
 
+extern "C" int som_filter_half_width(int K, double neighbourhood_range) {
+    if (K <= 0 || !(neighbourhood_range > 0.0)) return 0;
+    return host_band_half_width(two_var_of(neighbourhood_range), K);
+}
+
 extern "C" size_t som_filter_workspace_bytes(int K, int D, double neighbourhood_range) {
     if (K <= 0 || D <= 0 || !(neighbourhood_range > 0.0)) return 0;
     const float two_var = two_var_of(neighbourhood_range);

@@ -33,6 +33,7 @@ SIGNATURES = {
     "som_histogram_i64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "som_filter_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p]),
     "som_filter_workspace_bytes": (c_size_t, [c_int, c_int, c_double]),
+    "som_filter_half_width": (c_int, [c_int, c_double]),
     "som_filter_ws_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_size_t,
                                   c_void_p]),
     "som_accumulate_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
@@ -43,6 +44,15 @@ SIGNATURES = {
                                                c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "som_adam_dp_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double,
                                 c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "som_peer_signal_bytes": (c_size_t, []),
+    "som_peer_allreduce_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "som_peer_reduce_rows_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                         c_int, c_void_p, c_int, c_void_p]),
+    "som_peer_bcast_rows_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int,
+                                        c_void_p]),
+    "som_peer_adam_slice_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                        c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                        c_int, c_int, c_void_p, c_int, c_void_p]),
     "som_quantize_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int,
                                       c_int, c_int, c_void_p, c_void_p]),
     "som_adam_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,

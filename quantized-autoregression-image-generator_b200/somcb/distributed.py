@@ -39,17 +39,161 @@ def split_batch(feature_map, world_size, rank):
     return feature_map[lo:hi]
 
 
-class DataParallelSom(SomTrainer):
-    """SomTrainer whose accumulators are summed across the process group once per step."""
+class PeerMemory:
+    """Symmetric (peer-mapped + NVSwitch-multicast) device allocations of one process group.  torch's symmetric-memory
+    allocator is the plumbing (allocation, handle exchange, multicast binding); the kernels that use the addresses
+    are libsomcb's (som_peer_*)."""
 
-    def __init__(self, codebook, lr, neighbourhood_step, group=None, **kw):
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._sm = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.device = device
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._keep = []
+        sig = self.alloc(_default_ops.peer_signal_bytes() // 4, torch.int32)
+        sig[0].zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+        self.signal_ptrs = sig[2]
+
+    def alloc(self, numel, dtype=torch.float32):
+        """Returns (local tensor, multicast address or 0, list of peer addresses)."""
+        t = self._sm.empty(int(numel), dtype=dtype, device=self.device)
+        hdl = self._sm.rendezvous(t, self.group)
+        mc = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
+        self._keep.append((t, hdl))
+        return t, mc, [int(p) for p in hdl.buffer_ptrs]
+
+    @staticmethod
+    def available(device):
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+        except Exception:  # noqa: BLE001
+            return False
+        return torch.cuda.is_available() and torch.cuda.get_device_capability(device)[0] >= 9
+
+
+class DataParallelSom(SomTrainer):
+    """SomTrainer whose accumulators are summed across the process group once per step.
+
+    ``tail`` selects what follows the local accumulation:
+
+    * ``"nccl"``: ONE ``all_reduce`` of the packed buffer, then every rank runs both filters and Adam on the whole
+      codebook (replicated);
+    * ``"peer"``: the sharded tail over NVLink / NVSwitch multicast memory (csrc/som_peer.cu).  Rank r owns units
+      [lo_r, hi_r): it pulls the in-switch-reduced accumulator rows of its slice plus the filter's halo
+      (``som_peer_reduce_rows_f32``: the reduce-scatter half, with overlap), filters them, runs Adam on its rows and
+      stores the new rows into every rank's codebook (``som_peer_adam_slice_f32``: the all-gather fused into the
+      update); ``W~ = T @ W`` is computed per slice and broadcast the same way.  The non-shrinking part of a
+      strong-scaled step (two whole-codebook filters, Adam, a 4 MB all-reduce) becomes 1/R of the filters plus
+      three small kernels.  Falls back to one in-switch all-reduce (``som_peer_allreduce_f32``) + replicated tail when
+      the halo makes slicing pointless (slice + halo >= 3/4 of the units);
+    * ``"auto"`` (default): ``"peer"`` when symmetric memory with multicast is available, else ``"nccl"``.
+
+    Replicas stay bit-identical in every mode: a row is computed once, by its owner, and multicast."""
+
+    def __init__(self, codebook, lr, neighbourhood_step, group=None, tail="auto", **kw):
         self.group = group
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         super().__init__(codebook, lr, neighbourhood_step, world_size=world,
                          reduce_fn=self._allreduce if world > 1 else None, **kw)
+        self.tail = "nccl"
+        self.peer = None
+        w = codebook.codebook.weight
+        want_peer = tail in ("auto", "peer") and world > 1 and w.is_cuda and self.ops is _default_ops
+        if want_peer and codebook.embedding_dim % 4 == 0 and PeerMemory.available(w.device):
+            try:
+                self._setup_peer(w.device)
+            except Exception:  # noqa: BLE001
+                if tail == "peer":
+                    raise
+                self.peer = None
+        if tail == "peer" and self.peer is None and world > 1:
+            raise RuntimeError("DataParallelSom(tail='peer'): NVSwitch multicast symmetric memory is not available")
+
+    def _setup_peer(self, device):
+        cb = self.cb
+        k, d = cb.num_embeddings, cb.embedding_dim
+        pm = PeerMemory(self.group, device)
+        packed, mc_packed, _ = pm.alloc(k * d + 4)
+        w_sym, mc_w, _ = pm.alloc(k * d)
+        wt_sym, mc_wt, _ = pm.alloc(k * d)
+        if not (mc_packed and mc_w and mc_wt):
+            raise RuntimeError("no multicast support")
+        with torch.no_grad():
+            w_sym.copy_(cb.codebook.weight.data.reshape(-1))
+            cb.codebook.weight.data = w_sym.view(k, d)       # the parameter now lives in peer-mapped memory
+        cb._norm_cache = None
+        self.packed = packed
+        self.peer = pm
+        self._mc = {"packed": mc_packed, "w": mc_w, "wt": mc_wt}
+        self._wt = wt_sym.view(k, d)
+        self._tail_local = torch.empty(4, dtype=torch.float32, device=device)
+        self.tail = "peer"
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)
 
     def _allreduce(self, packed):
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _slices(self, h):
+        """(lo, hi, g0, g1) of this rank, the largest slice and the largest slice + halo of any rank."""
+        k = self.cb.num_embeddings
+        pm = self.peer
+        spans = [shard_bounds(k, pm.world, r) for r in range(pm.world)]
+        halo = [(max(0, lo - h), min(k, hi + h)) if hi > lo else (lo, lo) for lo, hi in spans]
+        lo, hi = spans[pm.rank]
+        g0, g1 = halo[pm.rank]
+        return lo, hi, g0, g1, max(b - a for a, b in spans), max(b - a for a, b in halo)
+
+    def _device_step(self, feature_map, bmu):
+        if self.peer is None:
+            return super()._device_step(feature_map, bmu)
+        ops, cb, pm = self.ops, self.cb, self.peer
+        w = cb.codebook.weight.data
+        x, geom = cb._input(feature_map)
+        k, d = cb.num_embeddings, cb.embedding_dim
+        rng = cb.neighbourhood_range
+        kd = k * d
+        lo, hi, g0, g1, max_own, max_halo = self._slices(ops.filter_half_width(k, rng))
+        sig, rank, world = pm.signal_ptrs, pm.rank, pm.world
+        sliced = 4 * max_halo <= 3 * k
+        if sliced:
+            # W~ rows of the own slice from W[g0:g1] (complete on every rank: the previous step ended with the barrier
+            # of the weight broadcast), multicast into every rank's W~
+            if hi > lo:
+                wth = ops.neighbourhood_filter(w[g0:g1], rng)
+                src = wth[lo - g0:hi - g0]
+            else:
+                src = self._tail_local[0:0]                  # no rows of its own: takes part in the barrier only
+            ops.peer_bcast_rows(src, self._mc["wt"] + lo * d * 4, max_own * d, rank, world, sig, 0)
+            wt = self._wt
+        else:
+            wt = ops.neighbourhood_filter(w, rng)
+        if bmu is None:
+            bmu = ops.bmu(x, geom, w, ops.prepare_codebook(w), variant=cb.bmu_variant)
+        ops.accumulate_packed(x, geom, bmu, wt, k, packed=self.packed)
+        if sliced:
+            rsum = torch.empty(max(1, g1 - g0), d, dtype=torch.float32, device=w.device)
+            ops.peer_reduce_rows(self._mc["packed"], k, d, g0, g1, max_halo, rsum, self._tail_local, rank, world, sig, 1)
+            if hi > lo:
+                gh = ops.neighbourhood_filter(rsum[:g1 - g0], rng, scale=1.0)
+                g_rows = gh[lo - g0:hi - g0]
+            else:
+                g_rows = self._tail_local[0:0]
+            loss = ops.peer_adam_slice(w[lo:hi], self._mc["w"] + lo * d * 4, self.m.data[lo:hi], self.v.data[lo:hi],
+                                       g_rows, max_own * d, d, self.lr, self.t_dev, self._tail_local, rank, world,
+                                       sig, 2, betas=self.betas, eps=self.eps)
+        else:
+            ops.peer_allreduce(self._mc["packed"], kd + 4, rank, world, sig, 1, w.device)
+            grad = ops.neighbourhood_filter(self.packed[:kd].view(k, d), rng, scale=1.0)
+            loss = ops.adam_step_dp(w, self.m, self.v, grad, d, self.lr, self.t_dev, self.packed[kd:],
+                                    betas=self.betas, eps=self.eps)
+        cb._norm_cache = None
+        self.last_bmu = bmu
+        return loss
 
     def broadcast_weights(self, src=0):
         """Make every replica start from rank ``src``'s codebook."""

@@ -308,3 +308,64 @@ def assemble_tokens(lr_idx, hr_idx, lr_num_embeddings, hr_num_embeddings, base_m
                                           1 if base_model else 0, _ptr(hr_input), _ptr(hr_target),
                                           _stream(hr_idx)))
     return hr_input, hr_target
+
+
+# ---- data-parallel tail over NVLink / NVSwitch peer memory (include/somcb.h, som_peer_*) -----------------------
+def filter_half_width(num_units, neighbourhood_range):
+    return int(_lib.load().som_filter_half_width(int(num_units), float(neighbourhood_range)))
+
+
+def peer_signal_bytes():
+    return int(_lib.load().som_peer_signal_bytes())
+
+
+def _pads(signal_ptrs):
+    import ctypes
+    return (ctypes.c_void_p * len(signal_ptrs))(*[int(p) for p in signal_ptrs])
+
+
+def peer_allreduce(mc_ptr, n, rank, world, signal_ptrs, channel, device):
+    """In-place all-reduce(sum) of ``n`` floats at the multicast address ``mc_ptr`` (every rank calls it)."""
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        check("som_peer_allreduce_f32",
+              lib.som_peer_allreduce_f32(int(mc_ptr), int(n), int(rank), int(world), _pads(signal_ptrs), int(channel),
+                                         torch.cuda.current_stream(device).cuda_stream))
+
+
+def peer_reduce_rows(mc_packed, num_units, dim, row0, row1, max_rows, out_rows, out_tail, rank, world, signal_ptrs,
+                     channel):
+    lib = _lib.load()
+    out_rows = _req(out_rows, torch.float32, "out_rows")
+    out_tail = _req(out_tail, torch.float32, "out_tail")
+    with torch.cuda.device(out_rows.device):
+        check("som_peer_reduce_rows_f32",
+              lib.som_peer_reduce_rows_f32(int(mc_packed), int(num_units), int(dim), int(row0), int(row1), int(max_rows),
+                                           _ptr(out_rows), _ptr(out_tail), int(rank), int(world), _pads(signal_ptrs),
+                                           int(channel), _stream(out_rows)))
+
+
+def peer_bcast_rows(src_rows, mc_dst, max_n, rank, world, signal_ptrs, channel):
+    lib = _lib.load()
+    src_rows = _req(src_rows, torch.float32, "src_rows")
+    with torch.cuda.device(src_rows.device):
+        check("som_peer_bcast_rows_f32",
+              lib.som_peer_bcast_rows_f32(_ptr(src_rows), int(mc_dst), src_rows.numel(), int(max_n), int(rank),
+                                          int(world), _pads(signal_ptrs), int(channel), _stream(src_rows)))
+
+
+def peer_adam_slice(w_rows, mc_w_rows, m_rows, v_rows, g_rows, max_n, dim, lr, steps_done, tail, rank, world,
+                    signal_ptrs, channel, loss_out=None, betas=(0.5, 0.999), eps=1e-8):
+    lib = _lib.load()
+    for t, nm in ((w_rows, "w_rows"), (m_rows, "m_rows"), (v_rows, "v_rows"), (g_rows, "g_rows"), (tail, "tail")):
+        _req(t, torch.float32, nm)
+    _req(steps_done, torch.int64, "steps_done")
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float64, device=w_rows.device)
+    with torch.cuda.device(w_rows.device):
+        check("som_peer_adam_slice_f32",
+              lib.som_peer_adam_slice_f32(_ptr(w_rows), int(mc_w_rows), _ptr(m_rows), _ptr(v_rows), _ptr(g_rows),
+                                          w_rows.numel(), int(max_n), int(dim), float(lr), float(betas[0]),
+                                          float(betas[1]), float(eps), _ptr(steps_done), _ptr(tail), _ptr(loss_out),
+                                          int(rank), int(world), _pads(signal_ptrs), int(channel), _stream(w_rows)))
+    return loss_out

@@ -35,8 +35,12 @@ def main():
     w0 = trained_like_codebook(k, pd, 7)
     batch = 64 * world
     dp_cb = make_cb(w0, pd, dev)
-    dp = somcb.DataParallelSom(dp_cb, lr=1e-4, neighbourhood_step=3)
+    dp = somcb.DataParallelSom(dp_cb, lr=1e-4, neighbourhood_step=3)           # tail="auto": peer memory when available
     dp.broadcast_weights(0)
+    dp_n_cb = make_cb(w0, pd, dev)
+    dp_n = somcb.DataParallelSom(dp_n_cb, lr=1e-4, neighbourhood_step=3, tail="nccl")
+    if rank == 0:
+        print(f"[dp] tail of the default trainer: {dp.tail}")
     ref_cb = make_cb(w0, pd, dev)
     ref = somcb.SomTrainer(ref_cb, lr=1e-4, neighbourhood_step=3)
     dp_g_cb = make_cb(w0, pd, dev)                          # the same steps through the captured CUDA graph
@@ -47,7 +51,10 @@ def main():
         x = synthetic_fmaps(n_f, 500 + step).to(dev)
         l_dp = dp.step(somcb.split_batch(x, world, rank).contiguous())
         l_g = dp_g.step(somcb.split_batch(x, world, rank).contiguous())
+        l_n = dp_n.step(somcb.split_batch(x, world, rank).contiguous())
         l_ref = ref.step(x)
+        rel_n = float((dp_n_cb.codebook.weight.data - ref_cb.codebook.weight.data).norm() / ref_cb.codebook.weight.data.norm())
+        ok &= rel_n <= 1e-6 and abs(float(l_n) - float(l_ref)) <= 1e-6 * abs(float(l_ref))
         same_g = torch.equal(dp_g_cb.codebook.weight.data, dp_cb.codebook.weight.data) and float(l_g) == float(l_dp)
         if rank == 0 and not same_g:
             print(f"[dp] step {step}: graph-replayed DP step differs from the eager DP step")
