@@ -365,7 +365,7 @@ def run_headline(args, dev, world, rank, peaks):
             tl = torch.empty(4, dtype=torch.float32, device=dev)
             wth = ops.neighbourhood_filter(w[g0:g1], rng)
             mm, vv = torch.zeros(hi_u - lo_u, d, device=dev), torch.zeros(hi_u - lo_u, d, device=dev)
-            ops.peer_reduce_rows(mc["packed"], k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1)
+            ops.peer_reduce_rows(mc["packed"], tr._peer_packed, k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1)
             gh = ops.neighbourhood_filter(rsum, rng)
             dist.barrier()
             for name in ("filter_W", "filter_Rbar", "adam"):
@@ -374,7 +374,7 @@ def run_headline(args, dev, world, rank, peaks):
             parts["slice: multicast W~ rows + barrier"] = _timed(
                 lambda: ops.peer_bcast_rows(wth[lo_u - g0:hi_u - g0], mc["wt"] + lo_u * d * 4, max_own * d, rk, world, sig, 0), reps)
             parts["slice: in-switch reduce of Rbar rows + halo"] = _timed(
-                lambda: ops.peer_reduce_rows(mc["packed"], k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1), reps)
+                lambda: ops.peer_reduce_rows(mc["packed"], tr._peer_packed, k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1), reps)
             parts["slice: filter_Rbar rows"] = _timed(lambda: ops.neighbourhood_filter(rsum, rng), reps)
             # (Adam here re-broadcasts the CURRENT rows: lr = 0 keeps the replicas' weights unchanged)
             parts["slice: adam + multicast W rows + barrier"] = _timed(

@@ -93,6 +93,18 @@ SOM_API int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd
                      int64_t* out_idx, float* out_rd,
                      void* ws, size_t ws_bytes, int variant, void* stream);
 
+/* The same search that ALSO writes stage_rows, a patch-major (n_patches, D) fp32 copy of the patch rows -- the
+ * (N, Seq, D) tensor patchify materialises in models/layers.py:8-34, here a by-product of the kernel that holds
+ * every row in registers anyway.  The training step's segmented gather (som_accumulate_*_nchw_f32 on the geometry
+ * (n_patches, 1, 1, D, 1, D)) then reads ONE contiguous row per patch instead of pH*C pieces of pW floats, which
+ * in NCHW cost a whole DRAM burst each.  Only the FP16-split kernel of 16 < D <= 256 emits it: ask
+ * som_bmu_can_stage (host-only) first; SOM_E_UNSUPPORTED otherwise.  stage_rows == NULL: som_bmu_nchw_f32.     */
+SOM_API int som_bmu_can_stage(int64_t n_patches, int D, int K, int variant);
+SOM_API int som_bmu_stage_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                           const float* W, const float* c_norm2, int K, int64_t unit_offset,
+                           int64_t* out_idx, float* out_rd, float* stage_rows,
+                           void* ws, size_t ws_bytes, int variant, void* stream);
+
 /* Same search on pre-flattened patch rows: `patches` is (n, D) row-major fp32 (what patchify +
  * reshape produce in models/Codebook.py:83-84).  Equivalent to som_bmu_nchw_f32 with the rows seen
  * as n one-patch images (n_img = n, C = 1, H = 1, W = D, pH = 1, pW = D).                       */
@@ -201,15 +213,20 @@ SOM_API int som_adam_dp_f32(float* W, float* m, float* v, const float* g, int64_
  * A peer that never arrives makes the kernel trap after ~4 s instead of hanging.                               */
 SOM_API size_t som_peer_signal_bytes(void);
 /* In-place all-reduce(sum) of n floats (n % 4 == 0): rank r reduces quads [r*n/4/world, ...) in the switch
- * (multimem.ld_reduce) and stores them to every rank (multimem.st).                                          */
-SOM_API int som_peer_allreduce_f32(void* mc_buf, int64_t n, int rank, int world, void* const* signal_pads,
-                           int channel, void* stream);
+ * (multimem.ld_reduce) and stores them to every rank (multimem.st).  With peer_bufs (HOST array of the buffer's
+ * `world` peer addresses) and local_buf (this rank's own address) the buffer is a packed accumulator buffer:
+ * its last 4 floats are the tail of som_accumulate_packed_nchw_f32 and are summed EXACTLY instead -- every rank
+ * reads the R tails through the peer addresses, adds them in rank order (squared error in fp64) and writes the
+ * result to its local tail (the in-switch fp32 adder is not exact enough for the loss).  Both NULL: plain data. */
+SOM_API int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer_bufs, float* local_buf, int rank,
+                           int world, void* const* signal_pads, int channel, void* stream);
 /* Rows [row0, row1) of the K x D accumulator matrix at mc_packed (layout of som_accumulate_packed_nchw_f32),
  * reduced over the ranks into LOCAL out_rows, and the reduced 4-float tail into LOCAL out_tail: the
  * reduce-scatter half of the all-reduce for a rank that owns a slice of units plus the filter's halo.
- * max_rows = the largest row1 - row0 of any rank.  Waits until every rank's accumulators are complete.       */
-SOM_API int som_peer_reduce_rows_f32(const void* mc_packed, int K, int D, int row0, int row1, int max_rows,
-                             float* out_rows, float* out_tail, int rank, int world,
+ * max_rows = the largest row1 - row0 of any rank.  Waits until every rank's accumulators are complete.  The tail
+ * is summed exactly through peer_packed (HOST array of the buffer's peer addresses), as in som_peer_allreduce_f32. */
+SOM_API int som_peer_reduce_rows_f32(const void* mc_packed, void* const* peer_packed, int K, int D, int row0,
+                             int row1, int max_rows, float* out_rows, float* out_tail, int rank, int world,
                              void* const* signal_pads, int channel, void* stream);
 /* n floats of local src_rows stored to mc_dst_rows on every rank, then a barrier over the ranks: when the call
  * has completed on a rank, every rank's rows have landed in its copy.  max_n = the largest n of any rank.      */

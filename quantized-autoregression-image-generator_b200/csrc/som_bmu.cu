@@ -11,9 +11,10 @@ int launch_bmu_ffma(const float* x, const Geom& g, const float* W, const float* 
 bool tc_supported(int64_t n_patches, int D, int K);
 size_t tc_workspace_bytes(int64_t n_patches, int D, int K, int arith);
 int tc_split_mode(int64_t n_patches, int D, int K, int arith);
+bool tc_can_stage(int64_t n_patches, int D, int K, int arith);
 int launch_bmu_tc(const float* x, const Geom& g, const float* W, const float* cn, int K,
-                  int64_t unit_offset, int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, int arith,
-                  cudaStream_t st);
+                  int64_t unit_offset, int64_t* out_idx, float* out_rd, float* stage, void* ws, size_t ws_bytes,
+                  int arith, cudaStream_t st);
 }  // namespace som
 
 using namespace som;
@@ -49,10 +50,24 @@ extern "C" size_t som_bmu_workspace_bytes(int64_t n_patches, int D, int K, int v
     return ffma_workspace_bytes(n_patches, K);
 }
 
+extern "C" int som_bmu_can_stage(int64_t n_patches, int D, int K, int variant) {
+    if (n_patches <= 0 || D <= 0 || K <= 0) return 0;
+    if (variant == SOM_BMU_AUTO) variant = som_bmu_pick_variant(n_patches, D, K);
+    return is_tc(variant) && tc_can_stage(n_patches, D, K, arith_of(variant)) ? 1 : 0;
+}
+
 extern "C" int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
                                 const float* W, const float* c_norm2, int K, int64_t unit_offset,
                                 int64_t* out_idx, float* out_rd,
                                 void* ws, size_t ws_bytes, int variant, void* stream) {
+    return som_bmu_stage_nchw_f32(x, n_img, C, H, Wd, pH, pW, W, c_norm2, K, unit_offset, out_idx, out_rd, nullptr, ws,
+                                  ws_bytes, variant, stream);
+}
+
+extern "C" int som_bmu_stage_nchw_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                                      const float* W, const float* c_norm2, int K, int64_t unit_offset,
+                                      int64_t* out_idx, float* out_rd, float* stage_rows,
+                                      void* ws, size_t ws_bytes, int variant, void* stream) {
     // an empty batch (torch hands out null data pointers for zero-element tensors) is a valid no-op: the reference
     // returns an empty int64 tensor for it (models/Codebook.py:77-99 on a (0, C, H, W) input)
     SOM_REQUIRE(W && c_norm2 && ((x && out_idx) || n_img == 0), SOM_E_BADARG, "bmu: null pointer");
@@ -66,9 +81,10 @@ extern "C" int som_bmu_nchw_f32(const float* x, int64_t n_img, int C, int H, int
     if (is_tc(variant)) {
         SOM_REQUIRE(tc_supported(g.n_patches, g.D, K), SOM_E_UNSUPPORTED,
                     "bmu: tensor-core variant does not support D=%d K=%d", g.D, K);
-        return launch_bmu_tc(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes, arith_of(variant),
-                             (cudaStream_t)stream);
+        return launch_bmu_tc(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, stage_rows, ws, ws_bytes,
+                             arith_of(variant), (cudaStream_t)stream);
     }
+    SOM_REQUIRE(stage_rows == nullptr, SOM_E_UNSUPPORTED, "bmu: the FFMA variant does not emit a staging copy");
     return launch_bmu_ffma(x, g, W, c_norm2, K, unit_offset, out_idx, out_rd, ws, ws_bytes,
                            (cudaStream_t)stream);
 }

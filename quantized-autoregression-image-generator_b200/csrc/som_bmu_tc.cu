@@ -26,7 +26,8 @@ int launch_bmu_tc_s(const float* x, const Geom& g, const float* W, const float* 
 bool tc_l16_applicable(int64_t n_patches, int D, int K, bool force);
 size_t tc_l16_workspace_bytes(int64_t n_patches, int D, int K, bool force);
 int launch_bmu_tc_l16(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
-                      int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, bool force, cudaStream_t st);
+                      int64_t* out_idx, float* out_rd, float* stage, void* ws, size_t ws_bytes, bool force,
+                      cudaStream_t st);
 // som_bmu_tc_l.cu
 size_t tc_l_workspace_bytes(int64_t n_patches, int D, int K);
 int launch_bmu_tc_l(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
@@ -65,14 +66,21 @@ size_t tc_workspace_bytes(int64_t n_patches, int D, int K, int arith) {
     return tc_l_workspace_bytes(n_patches, D, K);
 }
 
+// the kernels whose builders can also emit the patch-major staging copy (som_bmu_stage_nchw_f32)
+bool tc_can_stage(int64_t n_patches, int D, int K, int arith) {
+    return tc_supported(n_patches, D, K) && !tc_s_applicable(D) && use_l16(n_patches, D, K, arith);
+}
+
 int launch_bmu_tc(const float* x, const Geom& g, const float* W, const float* cn, int K,
-                  int64_t unit_offset, int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, int arith,
-                  cudaStream_t st) {
+                  int64_t unit_offset, int64_t* out_idx, float* out_rd, float* stage, void* ws, size_t ws_bytes,
+                  int arith, cudaStream_t st) {
     if (g.n_patches == 0) return SOM_OK;
+    SOM_REQUIRE(stage == nullptr || tc_can_stage(g.n_patches, g.D, K, arith), SOM_E_UNSUPPORTED,
+                "bmu: the kernel for this shape does not emit a staging copy (ask som_bmu_can_stage first)");
     if (tc_s_applicable(g.D))
         return launch_bmu_tc_s(x, g, W, cn, K, unit_offset, out_idx, out_rd, ws, ws_bytes, arith, st);
     if (use_l16(g.n_patches, g.D, K, arith))
-        return launch_bmu_tc_l16(x, g, W, cn, K, unit_offset, out_idx, out_rd, ws, ws_bytes, arith == 2, st);
+        return launch_bmu_tc_l16(x, g, W, cn, K, unit_offset, out_idx, out_rd, stage, ws, ws_bytes, arith == 2, st);
     SOM_REQUIRE(arith != 2, SOM_E_UNSUPPORTED, "bmu: no FP16-split kernel for D=%d K=%d (SOM_BMU_TC_F16)", g.D, K);
     return launch_bmu_tc_l(x, g, W, cn, K, unit_offset, out_idx, out_rd, ws, ws_bytes, st);
 }

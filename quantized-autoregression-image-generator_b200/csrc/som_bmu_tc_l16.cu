@@ -65,6 +65,7 @@ struct Params {
     const float* x;
     Geom g;
     const float* scale;     // [s_c, t_c] written by cb_scale_l_kernel earlier on the stream
+    float* stage;           // optional patch-major copy of the patch rows (n_patches x D), written by the builders
 };
 
 struct __align__(8) Barriers {
@@ -396,6 +397,21 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
             const float sp = __uint_as_float((uint32_t)(127 + es) << 23);
             for (int fb = 0; fb < DB; ++fb) {
                 if (DB > 1) load_blk(src, ok, fb);
+                if (P.stage != nullptr && ok) {
+                    // patch-major staging copy for the update's segmented gather: a patch is sixteen 16-byte pieces
+                    // in NCHW (P = 4) but ONE contiguous row here, and the builder holds it in registers anyway
+                    float* srow = P.stage + p * D + fb * 64;
+                    if ((D & 3) == 0) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            if (fb * 64 + c * 4 < D)
+                                *reinterpret_cast<float4*>(srow + c * 4) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 64; ++e)
+                            if (fb * 64 + e < D) srow[e] = v[e];
+                    }
+                }
                 const int u = i * DB + fb;
                 const int as = u % NA;
                 mbar_wait_warp<true>(&bars.a_empty[as], ((uint32_t)(u / NA) & 1u) ^ 1u, lane);
@@ -619,7 +635,8 @@ size_t tc_l16_workspace_bytes(int64_t n_patches, int D, int K, bool force) {
 }
 
 int launch_bmu_tc_l16(const float* x, const Geom& g, const float* W, const float* cn, int K, int64_t unit_offset,
-                      int64_t* out_idx, float* out_rd, void* ws, size_t ws_bytes, bool force, cudaStream_t st) {
+                      int64_t* out_idx, float* out_rd, float* stage, void* ws, size_t ws_bytes, bool force,
+                      cudaStream_t st) {
     using namespace tcl16;
     const int64_t n = g.n_patches;
     if (n == 0) return SOM_OK;
@@ -653,7 +670,7 @@ int launch_bmu_tc_l16(const float* x, const Geom& g, const float* W, const float
     Params P;
     P.DB = pl.DB; P.nks_last = pl.nks_last; P.NT = pl.NT; P.n_mtiles = pl.n_mtiles; P.NA = pl.NA; P.NB = pl.NB;
     P.K_pad = pl.K_pad; P.rows = n; P.unit_offset = unit_offset; P.out_idx = out_idx; P.out_rd = out_rd;
-    P.x = x; P.g = g; P.scale = scale;
+    P.x = x; P.g = g; P.scale = scale; P.stage = stage;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
     static const KernelFn kernels[4] = {bmu_tc_l16_kernel<1, false>, bmu_tc_l16_kernel<2, false>,

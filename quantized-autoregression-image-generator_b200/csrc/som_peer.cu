@@ -72,11 +72,36 @@ __device__ __forceinline__ void mm_st(float* mc, const float4& v) {
                  ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// in-place all-reduce of n4 float4 at the multicast address: rank r reduces and re-broadcasts quads [q0, q1)
-__global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q0, int64_t q1, Pads pads, int channel,
-                                                            int rank, int world) {
+// The 4-float tail [sse_hi, sse_lo, n / 4096, n % 4096] of the packed accumulator buffer is NOT reduced in the
+// switch: the in-switch fp32 adder is not exact enough for the loss (measured 1.2e-6 relative over 8 ranks), and the
+// patch count must be exact.  Every rank reads the R tails through the peer addresses and adds them in rank order,
+// the squared error in fp64 -- the same bits on every rank.
+__device__ __forceinline__ float4 exact_tail(const Pads& bufs, int64_t q_tail, int world) {
+    double sse = 0.0, cnt_hi = 0.0, cnt_lo = 0.0;
+    for (int r = 0; r < world; ++r) {
+        float4 t;
+        const float* p = reinterpret_cast<const float*>(bufs.p[r]) + 4 * q_tail;
+        asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p) : "memory");
+        sse += (double)t.x + (double)t.y;
+        cnt_hi += (double)t.z;
+        cnt_lo += (double)t.w;
+    }
+    const double cnt = cnt_hi * 4096.0 + cnt_lo;
+    const float hi = (float)sse;
+    const double c_hi = floor(cnt / 4096.0);
+    return make_float4(hi, (float)(sse - (double)hi), (float)c_hi, (float)(cnt - c_hi * 4096.0));
+}
+
+// in-place all-reduce of n4 float4 at the multicast address: rank r reduces and re-broadcasts quads [q0, q1);
+// q_tail >= 0: that quad is the packed buffer's tail, excluded from the in-switch part and summed exactly
+__global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q0, int64_t q1, int64_t q_tail,
+                                                            float4* __restrict__ tail_out, Pads bufs, Pads pads,
+                                                            int channel, int rank, int world) {
     sync_blocks<false, true>(pads, channel, rank, world);       // every rank's input is complete
     __syncthreads();
+    float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q_tail >= 0 && blockIdx.x == 0 && threadIdx.x == 0) tail = exact_tail(bufs, q_tail, world);
     const int64_t stride = (int64_t)gridDim.x * THREADS;
     for (int64_t q = q0 + blockIdx.x * (int64_t)THREADS + threadIdx.x; q < q1; q += 4 * stride) {
         float4 v[4];
@@ -88,14 +113,15 @@ __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q
             if (q + u * stride < q1) mm_st(mc + 4 * (q + u * stride), v[u]);
     }
     __syncthreads();
-    sync_blocks<true, true>(pads, channel, rank, world);        // every slice has landed everywhere
+    sync_blocks<true, true>(pads, channel, rank, world);        // every slice has landed everywhere (and every tail was read)
+    if (q_tail >= 0 && blockIdx.x == 0 && threadIdx.x == 0) *tail_out = tail;
 }
 
 // rows [q0, q1) (in float4 units of the K x D accumulator matrix) and the 4-float tail at quad q_tail, reduced over
 // the ranks into local memory
 __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(const float* mc, int64_t q0, int64_t q1, int64_t q_tail,
                                                               float4* __restrict__ out, float4* __restrict__ tail_out,
-                                                              Pads pads, int channel, int rank, int world) {
+                                                              Pads bufs, Pads pads, int channel, int rank, int world) {
     sync_blocks<false, true>(pads, channel, rank, world);       // every rank's accumulators are complete
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * THREADS;
@@ -108,7 +134,7 @@ __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(const float* mc, i
         for (int u = 0; u < 4; ++u)
             if (q + u * stride < q1) out[q + u * stride - q0] = v[u];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *tail_out = mm_ld_reduce(mc + 4 * q_tail);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *tail_out = exact_tail(bufs, q_tail, world);
 }
 
 // local rows -> the same rows of every rank (multicast store), then the cross-rank barrier that makes them visible
@@ -186,39 +212,52 @@ using namespace som::peer;
 
 extern "C" size_t som_peer_signal_bytes(void) { return (size_t)4 * MAX_BLOCKS * MAX_WORLD * sizeof(uint32_t); }
 
-extern "C" int som_peer_allreduce_f32(void* mc_buf, int64_t n, int rank, int world, void* const* signal_pads,
-                                      int channel, void* stream) {
+extern "C" int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer_bufs, float* local_buf, int rank,
+                                      int world, void* const* signal_pads, int channel, void* stream) {
     SOM_REQUIRE(mc_buf != nullptr && n >= 0 && n % 4 == 0 && ((uintptr_t)mc_buf & 15) == 0, SOM_E_BADARG,
                 "peer_allreduce: n=%lld must be a multiple of 4 floats, 16-byte aligned", (long long)n);
     SOM_REQUIRE(channel >= 0 && channel < 4, SOM_E_BADARG, "peer: channel=%d", channel);
-    Pads pads;
+    SOM_REQUIRE((peer_bufs == nullptr) == (local_buf == nullptr), SOM_E_BADARG,
+                "peer_allreduce: peer_bufs and local_buf go together");
+    Pads pads, bufs = {};
     int rc = make_pads(&pads, signal_pads, rank, world);
     if (rc) return rc;
-    const int64_t n4 = n / 4, per = ceil_div64(n4, world);
+    int64_t n4 = n / 4, q_tail = -1;
+    if (peer_bufs != nullptr) {                      // packed accumulator buffer: the last quad is the exact tail
+        SOM_REQUIRE(n4 >= 1, SOM_E_BADARG, "peer_allreduce: packed buffer without a tail");
+        rc = make_pads(&bufs, peer_bufs, rank, world);
+        if (rc) return rc;
+        q_tail = --n4;
+    }
+    const int64_t per = ceil_div64(n4, world);
     const int64_t q0 = per * rank < n4 ? per * rank : n4, q1 = q0 + per < n4 ? q0 + per : n4;
     // the grid must be the same on every rank (blocks pair up across ranks): size it for the largest slice
-    allreduce_kernel<<<grid_for(per), THREADS, 0, (cudaStream_t)stream>>>((float*)mc_buf, q0, q1, pads, channel, rank, world);
+    allreduce_kernel<<<grid_for(per), THREADS, 0, (cudaStream_t)stream>>>(
+        (float*)mc_buf, q0, q1, q_tail, q_tail >= 0 ? (float4*)(local_buf + 4 * q_tail) : nullptr, bufs, pads, channel,
+        rank, world);
     return check_launch("peer_allreduce_kernel");
 }
 
-extern "C" int som_peer_reduce_rows_f32(const void* mc_packed, int K, int D, int row0, int row1, int max_rows,
-                                        float* out_rows, float* out_tail, int rank, int world,
+extern "C" int som_peer_reduce_rows_f32(const void* mc_packed, void* const* peer_packed, int K, int D, int row0,
+                                        int row1, int max_rows, float* out_rows, float* out_tail, int rank, int world,
                                         void* const* signal_pads, int channel, void* stream) {
-    SOM_REQUIRE(mc_packed && out_rows && out_tail, SOM_E_BADARG, "peer_reduce_rows: null pointer");
+    SOM_REQUIRE(mc_packed && peer_packed && out_rows && out_tail, SOM_E_BADARG, "peer_reduce_rows: null pointer");
     SOM_REQUIRE(K > 0 && D > 0 && D % 4 == 0 && row0 >= 0 && row0 <= row1 && row1 <= K && max_rows >= row1 - row0,
                 SOM_E_BADARG, "peer_reduce_rows: K=%d D=%d rows [%d, %d) max %d (D must be a multiple of 4)", K, D,
                 row0, row1, max_rows);
     SOM_REQUIRE((((uintptr_t)mc_packed | (uintptr_t)out_rows | (uintptr_t)out_tail) & 15) == 0, SOM_E_BADARG,
                 "peer_reduce_rows: buffers must be 16-byte aligned");
     SOM_REQUIRE(channel >= 0 && channel < 4, SOM_E_BADARG, "peer: channel=%d", channel);
-    Pads pads;
+    Pads pads, bufs;
     int rc = make_pads(&pads, signal_pads, rank, world);
+    if (rc) return rc;
+    rc = make_pads(&bufs, peer_packed, rank, world);
     if (rc) return rc;
     const int64_t d4 = D / 4;
     // same grid on every rank: sized from max_rows, the largest row count any rank reduces
     reduce_rows_kernel<<<grid_for((int64_t)max_rows * d4), THREADS, 0, (cudaStream_t)stream>>>(
         (const float*)mc_packed, (int64_t)row0 * d4, (int64_t)row1 * d4, (int64_t)K * d4, (float4*)out_rows,
-        (float4*)out_tail, pads, channel, rank, world);
+        (float4*)out_tail, bufs, pads, channel, rank, world);
     return check_launch("peer_reduce_rows_kernel");
 }
 

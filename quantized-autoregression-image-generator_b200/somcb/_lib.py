@@ -25,6 +25,10 @@ SIGNATURES = {
     "som_bmu_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_int, c_void_p]),
+    "som_bmu_can_stage": (c_int, [c_int64, c_int, c_int, c_int]),
+    "som_bmu_stage_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_int, c_void_p]),
     "som_bmu_flat_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_int, c_void_p]),
     "som_backward_nchw_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
@@ -45,9 +49,9 @@ SIGNATURES = {
     "som_adam_dp_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double,
                                 c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "som_peer_signal_bytes": (c_size_t, []),
-    "som_peer_allreduce_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
-    "som_peer_reduce_rows_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
-                                         c_int, c_void_p, c_int, c_void_p]),
+    "som_peer_allreduce_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "som_peer_reduce_rows_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_int, c_int, c_void_p, c_int, c_void_p]),
     "som_peer_bcast_rows_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int,
                                         c_void_p]),
     "som_peer_adam_slice_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,

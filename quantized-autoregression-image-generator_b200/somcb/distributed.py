@@ -117,7 +117,7 @@ class DataParallelSom(SomTrainer):
         cb = self.cb
         k, d = cb.num_embeddings, cb.embedding_dim
         pm = PeerMemory(self.group, device)
-        packed, mc_packed, _ = pm.alloc(k * d + 4)
+        packed, mc_packed, peer_packed = pm.alloc(k * d + 4)
         w_sym, mc_w, _ = pm.alloc(k * d)
         wt_sym, mc_wt, _ = pm.alloc(k * d)
         if not (mc_packed and mc_w and mc_wt):
@@ -129,6 +129,7 @@ class DataParallelSom(SomTrainer):
         self.packed = packed
         self.peer = pm
         self._mc = {"packed": mc_packed, "w": mc_w, "wt": mc_wt}
+        self._peer_packed = peer_packed
         self._wt = wt_sym.view(k, d)
         self._tail_local = torch.empty(4, dtype=torch.float32, device=device)
         self.tail = "peer"
@@ -172,12 +173,14 @@ class DataParallelSom(SomTrainer):
             wt = self._wt
         else:
             wt = ops.neighbourhood_filter(w, rng)
+        x_acc, geom_acc = x, geom
         if bmu is None:
-            bmu = ops.bmu(x, geom, w, ops.prepare_codebook(w), variant=cb.bmu_variant)
-        ops.accumulate_packed(x, geom, bmu, wt, k, packed=self.packed)
+            bmu, x_acc, geom_acc = self._search(x, geom, w)
+        ops.accumulate_packed(x_acc, geom_acc, bmu, wt, k, packed=self.packed)
         if sliced:
             rsum = torch.empty(max(1, g1 - g0), d, dtype=torch.float32, device=w.device)
-            ops.peer_reduce_rows(self._mc["packed"], k, d, g0, g1, max_halo, rsum, self._tail_local, rank, world, sig, 1)
+            ops.peer_reduce_rows(self._mc["packed"], self._peer_packed, k, d, g0, g1, max_halo, rsum, self._tail_local,
+                                 rank, world, sig, 1)
             if hi > lo:
                 gh = ops.neighbourhood_filter(rsum[:g1 - g0], rng, scale=1.0)
                 g_rows = gh[lo - g0:hi - g0]
@@ -187,7 +190,8 @@ class DataParallelSom(SomTrainer):
                                        g_rows, max_own * d, d, self.lr, self.t_dev, self._tail_local, rank, world,
                                        sig, 2, betas=self.betas, eps=self.eps)
         else:
-            ops.peer_allreduce(self._mc["packed"], kd + 4, rank, world, sig, 1, w.device)
+            ops.peer_allreduce(self._mc["packed"], kd + 4, rank, world, sig, 1, w.device,
+                               peer_ptrs=self._peer_packed, local=self.packed)
             grad = ops.neighbourhood_filter(self.packed[:kd].view(k, d), rng, scale=1.0)
             loss = ops.adam_step_dp(w, self.m, self.v, grad, d, self.lr, self.t_dev, self.packed[kd:],
                                     betas=self.betas, eps=self.eps)

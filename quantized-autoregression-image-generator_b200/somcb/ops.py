@@ -87,10 +87,16 @@ def prepare_codebook(weight, out=None):
     return out
 
 
+def bmu_can_stage(geom, num_units, variant=SOM_BMU_AUTO):
+    """Whether the BMU kernel for this shape can also emit the patch-major staging copy (``bmu(stage=...)``)."""
+    return bool(_lib.load().som_bmu_can_stage(n_patches_of(geom), dim_of(geom), int(num_units), int(variant)))
+
+
 def bmu(x, geom, weight, c_norm2=None, unit_offset=0, want_rd=False, variant=SOM_BMU_AUTO,
-        out=None):
+        out=None, stage=None):
     """K1.  x: fp32 contiguous buffer described by ``geom``.  Returns idx (n_patches,) int64
-    [and the reduced distance rd (n_patches,) fp32 when ``want_rd``]."""
+    [and the reduced distance rd (n_patches,) fp32 when ``want_rd``].  ``stage``: optional (n_patches, D) fp32
+    tensor that receives the patch-major copy of the patch rows (only where ``bmu_can_stage``)."""
     lib = _lib.load()
     x = _req(x, torch.float32, "x")
     w = _req(weight, torch.float32, "weight")
@@ -106,11 +112,15 @@ def bmu(x, geom, weight, c_norm2=None, unit_offset=0, want_rd=False, variant=SOM
     if out is None:
         out = torch.empty(npat, dtype=torch.int64, device=x.device)
     rd = torch.empty(npat, dtype=torch.float32, device=x.device) if want_rd else None
+    if stage is not None:
+        stage = _req(stage, torch.float32, "stage")
+        if stage.numel() != npat * d:
+            raise ValueError("stage must hold n_patches x D floats")
     with torch.cuda.device(x.device):
         ws, ws_bytes = _workspace(lib.som_bmu_workspace_bytes(npat, d, k, variant), x.device)
-        check("som_bmu_nchw_f32",
-              lib.som_bmu_nchw_f32(_ptr(x), *geom, _ptr(w), _ptr(c_norm2), k, int(unit_offset),
-                                   _ptr(out), _ptr(rd), _ptr(ws), ws_bytes, variant, _stream(x)))
+        check("som_bmu_stage_nchw_f32",
+              lib.som_bmu_stage_nchw_f32(_ptr(x), *geom, _ptr(w), _ptr(c_norm2), k, int(unit_offset),
+                                         _ptr(out), _ptr(rd), _ptr(stage), _ptr(ws), ws_bytes, variant, _stream(x)))
     return (out, rd) if want_rd else out
 
 
@@ -324,23 +334,27 @@ def _pads(signal_ptrs):
     return (ctypes.c_void_p * len(signal_ptrs))(*[int(p) for p in signal_ptrs])
 
 
-def peer_allreduce(mc_ptr, n, rank, world, signal_ptrs, channel, device):
-    """In-place all-reduce(sum) of ``n`` floats at the multicast address ``mc_ptr`` (every rank calls it)."""
+def peer_allreduce(mc_ptr, n, rank, world, signal_ptrs, channel, device, peer_ptrs=None, local=None):
+    """In-place all-reduce(sum) of ``n`` floats at the multicast address ``mc_ptr`` (every rank calls it).  With
+    ``peer_ptrs`` / ``local`` (the buffer's peer addresses and this rank's tensor) the buffer is a packed accumulator
+    buffer whose 4-float tail is summed exactly."""
     lib = _lib.load()
     with torch.cuda.device(device):
         check("som_peer_allreduce_f32",
-              lib.som_peer_allreduce_f32(int(mc_ptr), int(n), int(rank), int(world), _pads(signal_ptrs), int(channel),
+              lib.som_peer_allreduce_f32(int(mc_ptr), int(n), _pads(peer_ptrs) if peer_ptrs is not None else None,
+                                         _ptr(local), int(rank), int(world), _pads(signal_ptrs), int(channel),
                                          torch.cuda.current_stream(device).cuda_stream))
 
 
-def peer_reduce_rows(mc_packed, num_units, dim, row0, row1, max_rows, out_rows, out_tail, rank, world, signal_ptrs,
-                     channel):
+def peer_reduce_rows(mc_packed, peer_ptrs, num_units, dim, row0, row1, max_rows, out_rows, out_tail, rank, world,
+                     signal_ptrs, channel):
     lib = _lib.load()
     out_rows = _req(out_rows, torch.float32, "out_rows")
     out_tail = _req(out_tail, torch.float32, "out_tail")
     with torch.cuda.device(out_rows.device):
         check("som_peer_reduce_rows_f32",
-              lib.som_peer_reduce_rows_f32(int(mc_packed), int(num_units), int(dim), int(row0), int(row1), int(max_rows),
+              lib.som_peer_reduce_rows_f32(int(mc_packed), _pads(peer_ptrs), int(num_units), int(dim), int(row0),
+                                           int(row1), int(max_rows),
                                            _ptr(out_rows), _ptr(out_tail), int(rank), int(world), _pads(signal_ptrs),
                                            int(channel), _stream(out_rows)))
 

@@ -131,10 +131,11 @@ class SomTrainer:
         kd = k * d
 
         wt = ops.neighbourhood_filter(w, rng)
+        x_acc, geom_acc = x, geom
         if bmu is None:
-            bmu = ops.bmu(x, geom, w, ops.prepare_codebook(w), variant=cb.bmu_variant)
+            bmu, x_acc, geom_acc = self._search(x, geom, w)
         packed = self.packed
-        ops.accumulate_packed(x, geom, bmu, wt, k, packed=packed)
+        ops.accumulate_packed(x_acc, geom_acc, bmu, wt, k, packed=packed)
         if self.reduce_fn is not None:
             # ONE collective per step: Rbar, the squared error (float pair) and the patch count travel together
             self.reduce_fn(packed)
@@ -144,6 +145,20 @@ class SomTrainer:
         cb._norm_cache = None                          # W changed under torch's feet
         self.last_bmu = bmu
         return loss
+
+    def _search(self, x, geom, w):
+        """BMU search of the step.  Where the kernel can emit it, also the patch-major staging copy of the patch rows:
+        the segmented gather of the update then reads one contiguous row per patch (returns the buffer and geometry
+        the accumulation should read: the staging rows, or x itself)."""
+        ops, cb = self.ops, self.cb
+        cn = ops.prepare_codebook(w)
+        can = getattr(ops, "bmu_can_stage", None)
+        if can is not None and ops.n_patches_of(geom) > 0 and can(geom, cb.num_embeddings, cb.bmu_variant):
+            npat, d = ops.n_patches_of(geom), ops.dim_of(geom)
+            stage = torch.empty(npat, d, dtype=torch.float32, device=x.device)
+            bmu = ops.bmu(x, geom, w, cn, variant=cb.bmu_variant, stage=stage)
+            return bmu, stage, ops.flat_geometry(npat, d)
+        return ops.bmu(x, geom, w, cn, variant=cb.bmu_variant), x, geom
 
     def checkpoint_dict(self, image_channel):
         """The reference's checkpoint layout (train_codebook.py:271-278)."""

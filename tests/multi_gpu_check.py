@@ -69,6 +69,29 @@ def main():
                   f"range {dp_cb.neighbourhood_range}")
         ok &= rel_l <= 1e-6 and rel_w <= 1e-6 and same and dp_cb.neighbourhood_range == ref_cb.neighbourhood_range
 
+    # ---- in-switch all-reduce (multimem.ld_reduce / multimem.st) against the fp64 sum ----------------------
+    if dp.peer is not None:
+        pm = dp.peer
+        n = 1 << 20
+        buf, mc, _ = pm.alloc(n)
+        g = torch.Generator(device=dev).manual_seed(900 + rank)
+        buf.copy_(torch.randn(n, generator=g, device=dev) * (10.0 ** (rank % 3)))
+        parts = [torch.empty(n, device=dev) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        want = torch.stack(parts).double().sum(dim=0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ops.peer_allreduce(mc, n, pm.rank, pm.world, pm.signal_ptrs, 3, dev)
+        torch.cuda.synchronize()
+        err = float((buf.double() - want).abs().max() / want.abs().max())
+        chk = [torch.empty(n, device=dev) for _ in range(world)]
+        dist.all_gather(chk, buf)
+        same = all(torch.equal(chk[0], c) for c in chk)
+        if rank == 0:
+            print(f"[peer] in-switch all-reduce of 2^20 floats: max error {err:.2e} of the largest sum, "
+                  f"identical on every rank: {same}")
+        ok &= err <= 1e-6 and same
+
     # ---- unit-sharded search + histogram ---------------------------------------------------------
     pd, k = (8, 8), 8192
     w = trained_like_codebook(k, pd, 3).to(dev)

@@ -359,3 +359,30 @@ def test_packed_accumulate_and_device_scaled_adam_match_the_host_scaled_path():
         assert torch.equal(w_a, w_b) and torch.equal(v_a, v_b)
     assert int(t_dev) == 3
     assert abs(float(loss) - float(sse) / numel) <= 1e-12 * float(loss)
+
+
+def test_staging_copy_from_the_bmu_kernel_feeds_the_accumulation():
+    """Large batches of 16 < D <= 256: the FP16-split BMU kernel also writes the patch-major copy of the patch rows
+    (som_bmu_stage_nchw_f32); the copy equals patchify(x) bit for bit, the accumulation from it equals the
+    accumulation from NCHW bit for bit, and a trainer step through it matches the step that reads NCHW."""
+    from oracle.step_oracle import synthetic_fmaps, trained_like_codebook
+    for p, k, n_f in ((4, 2048, 320), (8, 1024, 1200)):
+        pd, d = (p, p), 4 * p * p
+        x = synthetic_fmaps(n_f, 31).to(DEV)
+        w = trained_like_codebook(k, pd, 7).to(DEV)
+        geom = ops.geometry(x.shape, pd)
+        npat = ops.n_patches_of(geom)
+        assert ops.bmu_can_stage(geom, k)
+        stage = torch.empty(npat, d, device=DEV)
+        idx = ops.bmu(x, geom, w, stage=stage)
+        assert torch.equal(idx, ops.bmu(x, geom, w))
+        assert torch.equal(stage, somcb.patchify(x, pd).reshape(npat, d))
+        wt = ops.neighbourhood_filter(w, k // 4)
+        a = ops.accumulate_packed(x, geom, idx, wt, k)
+        b = ops.accumulate_packed(stage, ops.flat_geometry(npat, d), idx, wt, k)
+        assert torch.equal(a, b)
+    assert not ops.bmu_can_stage(ops.geometry((8, 4, 32, 32), (4, 4)), 1024)      # small batch: 3xTF32 kernel
+    with pytest.raises(somcb._lib.SomError):
+        xs = synthetic_fmaps(8, 1).to(DEV)
+        g8 = ops.geometry(xs.shape, (4, 4))
+        ops.bmu(xs, g8, trained_like_codebook(1024, (4, 4), 7).to(DEV), stage=torch.empty(512, 64, device=DEV))
