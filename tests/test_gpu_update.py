@@ -366,7 +366,7 @@ def test_staging_copy_from_the_bmu_kernel_feeds_the_accumulation():
     (som_bmu_stage_nchw_f32); the copy equals patchify(x) bit for bit, the accumulation from it equals the
     accumulation from NCHW bit for bit, and a trainer step through it matches the step that reads NCHW."""
     from oracle.step_oracle import synthetic_fmaps, trained_like_codebook
-    for p, k, n_f in ((4, 2048, 320), (8, 1024, 1200)):
+    for p, k, n_f in ((4, 2048, 320), (8, 1024, 2400)):
         pd, d = (p, p), 4 * p * p
         x = synthetic_fmaps(n_f, 31).to(DEV)
         w = trained_like_codebook(k, pd, 7).to(DEV)
