@@ -217,7 +217,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 40))
-    base, s_per_step = _cpu_reference_step(steps, min(args.warmup, 2))
+    base, s_per_step = _cpu_reference_step(steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -342,7 +342,7 @@ def run_headline(args, dev, world, rank, peaks):
     packed = torch.empty(k * d + 4, dtype=torch.float32, device=dev)
     ops.accumulate_packed(x, geom, bmu, wt, k, packed=packed)
     wc, mc, vc = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
-    tdev = torch.ones(1, dtype=torch.int64, device=dev)
+    tdev = torch.tensor([1, 0], dtype=torch.int64, device=dev)
     grad = ops.neighbourhood_filter(packed[:k * d].view(k, d), rng)
     reps = 10
     parts = {"filter_W": _timed(lambda: ops.neighbourhood_filter(w, rng), reps),
@@ -403,13 +403,14 @@ def run_headline(args, dev, world, rank, peaks):
         with open(tpath) as f:
             tj = json.load(f)
         key = "bmu_c4_f16" if f16 else "bmu_c4"
-        traffic = tj.get(key + "_dram_bytes_per_launch")
+        per_patch = tj.get(key + "_dram_bytes_per_patch")
+        traffic = per_patch * n_local if per_patch else None
         pipe_pct = tj.get(key + "_tensor_pipe_active_pct")
         src = tj.get(key + "_source")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
                 "frac": achieved / peak_burst, "traffic": traffic,
-                "traffic_source": (f"constant from {src} (one ncu --set full capture at N=1), not measured in this run"
-                                   if traffic is not None else None),
+                "traffic_source": (f"DRAM bytes per patch of one ncu --set full capture x the patches of this launch: "
+                                   f"{src}; not measured in this run" if traffic is not None else None),
                 "kernel": ("bmu_tc_l16 (tcgen05 kind::f16, FP16 hi/lo split x3 products, fp32 accumulate in TMEM)" if f16
                            else "bmu_tc_l (tcgen05 kind::tf32 x3)"),
                 "peak_basis": (f"{peaks['_source']}: BURST cuBLAS bf16 {peaks['bf16_tflops']} TFLOP/s / 3 (three 16-bit "

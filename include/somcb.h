@@ -197,7 +197,10 @@ SOM_API int som_adam_devstep_f32(float* W, float* m, float* v, const float* g, i
  * the all-reduced accumulators) and `tail` the all-reduced 4-float tail of som_accumulate_packed_nchw_f32.  Applies
  * g * (float)(2 / numel), numel = D * n_global (F.mse_loss's mean, train_codebook.py:233-235) and the Adam rule of
  * som_adam_devstep_f32; writes loss = sse / numel to loss_out (device double, may be NULL).  Everything the host
- * would have to wait for stays on the device, so the whole step can be captured in a CUDA graph.            */
+ * would have to wait for stays on the device, so the whole step can be captured in a CUDA graph.
+ * steps_done points to TWO int64: [0] the number of completed steps (t = steps_done[0] + 1 is used, then it is
+ * incremented by the kernel itself), [1] a scratch word the kernel uses as its block-arrival counter: zero it once,
+ * the kernel leaves it at zero.                                                                               */
 SOM_API int som_adam_dp_f32(float* W, float* m, float* v, const float* g, int64_t n, int D,
                     double lr, double b1, double b2, double eps, int64_t* steps_done,
                     const float* tail, double* loss_out, void* stream);
@@ -234,7 +237,7 @@ SOM_API int som_peer_bcast_rows_f32(const float* src_rows, void* mc_dst_rows, in
                             int world, void* const* signal_pads, int channel, void* stream);
 /* som_adam_dp_f32 on the n weights of this rank's rows (all pointers address the slice; W_rows is this rank's
  * local copy, read) with the updated rows stored to mc_W_rows on EVERY rank -- the all-gather fused into the
- * update -- then the barrier over the ranks.                                                                 */
+ * update -- then the barrier over the ranks.  steps_done: two int64 as for som_adam_dp_f32.                   */
 SOM_API int som_peer_adam_slice_f32(const float* W_rows, void* mc_W_rows, float* m_rows, float* v_rows,
                             const float* g_rows, int64_t n, int64_t max_n, int D, double lr, double b1,
                             double b2, double eps, int64_t* steps_done, const float* tail, double* loss_out,

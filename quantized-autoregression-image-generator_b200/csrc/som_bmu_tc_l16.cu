@@ -524,6 +524,7 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 //   s_c = 2^(7 - floor(log2 sqrt(M2)))        so that  128 <= s_c max||c|| < 256, hence max |s_c c| < 256
 //   t_c = 2^(14 - floor(log2 (s_c M2)))       so that  max t_c s_c ||c||^2 in [2^14, 2^15)  (FP16 tops out at 65504)
 // An all-zero or non-finite codebook keeps both at 1.  One CTA over the K norms.
+__device__ __forceinline__ void scales_from_max_norm(float mn, float* out2);
 __global__ void __launch_bounds__(1024) cb_scale_l_kernel(const float* __restrict__ cn, int K, float* __restrict__ scale_out) {
     __shared__ float sh[32];
     float mn = 0.f;
@@ -534,37 +535,60 @@ __global__ void __launch_bounds__(1024) cb_scale_l_kernel(const float* __restric
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 32; ++w) mn = fmaxf(mn, sh[w]);
-        // a NaN norm is dropped by fmaxf; an infinite one shows up as exponent 0xff
-        const int en = (int)((__float_as_uint(mn) >> 23) & 0xffu);
-        int e = 0, g = 0;
-        if (mn > 0.f && en != 0xff && en != 0) {
-            const int e2 = en - 127;                                     // M2 in [2^e2, 2^(e2+1))
-            const int fl = (e2 >= 0) ? (e2 >> 1) : -((1 - e2) >> 1);     // floor(e2 / 2) = floor(log2 sqrt(M2))
-            e = 7 - fl;
-            e = e > 60 ? 60 : (e < -60 ? -60 : e);
-            g = 14 - (e2 + e);
-            g = g > 60 ? 60 : (g < -60 ? -60 : g);
-        }
-        scale_out[0] = __uint_as_float((uint32_t)(127 + e) << 23);
-        scale_out[1] = __uint_as_float((uint32_t)(127 + g) << 23);
+        scales_from_max_norm(mn, scale_out);
     }
 }
 
 // Pre-split codebook, FP16: row j = [ hi(-2 s_c c) for every 64-feature block | lo(..) for every block ] (halves,
 // zero beyond D); tail rows = 16 halves [n1 n2 n3 0..] of t_c s_c ||c||^2.  Rows >= K repeat unit K - 1: a padding
 // unit then never beats a real one (ties go to the lower index), whatever the patch holds.
-// One thread per (row, pair of features).
+// One thread per (row, pair of features).  OWN_SCALE (codebooks of up to 32 768 units): every CTA derives the two
+// scales itself from the K norms (L2-resident) instead of waiting for cb_scale_l_kernel -- one launch fewer on the
+// per-step critical path; CTA 0 publishes them for the search kernel.
+__device__ __forceinline__ void scales_from_max_norm(float mn, float* out2) {
+    // a NaN norm is dropped by fmaxf; an infinite one shows up as exponent 0xff
+    const int en = (int)((__float_as_uint(mn) >> 23) & 0xffu);
+    int e = 0, g = 0;
+    if (mn > 0.f && en != 0xff && en != 0) {
+        const int e2 = en - 127;                                     // M2 in [2^e2, 2^(e2+1))
+        const int fl = (e2 >= 0) ? (e2 >> 1) : -((1 - e2) >> 1);     // floor(e2 / 2) = floor(log2 sqrt(M2))
+        e = 7 - fl;
+        e = e > 60 ? 60 : (e < -60 ? -60 : e);
+        g = 14 - (e2 + e);
+        g = g > 60 ? 60 : (g < -60 ? -60 : g);
+    }
+    out2[0] = __uint_as_float((uint32_t)(127 + e) << 23);
+    out2[1] = __uint_as_float((uint32_t)(127 + g) << 23);
+}
+
+template <bool OWN_SCALE>
 __global__ void __launch_bounds__(256) split_w_l16_kernel(const float* __restrict__ W, const float* __restrict__ cn,
                                                           int K, int D, int DB, int K_pad,
-                                                          const float* __restrict__ scale, __half* __restrict__ Bp,
+                                                          float* __restrict__ scale, __half* __restrict__ Bp,
                                                           __half* __restrict__ Tp) {
+    __shared__ float sh_max[8];
+    __shared__ float sh_scale[2];
+    if (OWN_SCALE) {
+        float mn = 0.f;
+        for (int i = threadIdx.x; i < K; i += 256) mn = fmaxf(mn, fabsf(__ldg(cn + i)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmaxf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if ((threadIdx.x & 31) == 0) sh_max[threadIdx.x >> 5] = mn;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) mn = fmaxf(mn, sh_max[w]);
+            scales_from_max_norm(mn, sh_scale);
+            if (blockIdx.x == 0) { scale[0] = sh_scale[0]; scale[1] = sh_scale[1]; }
+        }
+        __syncthreads();
+    }
     const int pairs = DB * 32;
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= (int64_t)K_pad * pairs) return;
     const int row = (int)(t / pairs);
     const int d = (int)(t - (int64_t)row * pairs) * 2;
     const int src = row < K ? row : K - 1;
-    const float sc = scale[0], tcs = scale[1];
+    const float sc = OWN_SCALE ? sh_scale[0] : scale[0], tcs = OWN_SCALE ? sh_scale[1] : scale[1];
     float v0 = 0.f, v1 = 0.f;
     if (d < D) v0 = -2.0f * sc * W[(int64_t)src * D + d];                   // exact scaling
     if (d + 1 < D) v1 = -2.0f * sc * W[(int64_t)src * D + d + 1];
@@ -649,12 +673,18 @@ int launch_bmu_tc_l16(const float* x, const Geom& g, const float* W, const float
     __half* Bp = (__half*)((char*)ws + pl.off_b);
     __half* Tp = (__half*)((char*)ws + pl.off_t);
     float* scale = (float*)((char*)ws + pl.off_s);
-    cb_scale_l_kernel<<<1, 1024, 0, st>>>(cn, K, scale);
-    int rc = check_launch("cb_scale_l_kernel");
-    if (rc) return rc;
+    int rc;
     {
         const int64_t items = (int64_t)pl.K_pad * pl.DB * 32;
-        split_w_l16_kernel<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(W, cn, K, g.D, pl.DB, pl.K_pad, scale, Bp, Tp);
+        const unsigned blocks = (unsigned)ceil_div64(items, 256);
+        if (K <= 32768) {
+            split_w_l16_kernel<true><<<blocks, 256, 0, st>>>(W, cn, K, g.D, pl.DB, pl.K_pad, scale, Bp, Tp);
+        } else {
+            cb_scale_l_kernel<<<1, 1024, 0, st>>>(cn, K, scale);
+            rc = check_launch("cb_scale_l_kernel");
+            if (rc) return rc;
+            split_w_l16_kernel<false><<<blocks, 256, 0, st>>>(W, cn, K, g.D, pl.DB, pl.K_pad, scale, Bp, Tp);
+        }
         rc = check_launch("split_w_l16_kernel");
         if (rc) return rc;
     }

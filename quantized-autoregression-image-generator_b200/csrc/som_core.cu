@@ -498,9 +498,9 @@ __global__ void step_bump_kernel(int64_t* steps_done) { *steps_done += 1; }
 __global__ void __launch_bounds__(256) adam_dp_kernel(float* __restrict__ W, float* __restrict__ m,
                                                       float* __restrict__ v, const float* __restrict__ g,
                                                       int64_t n, int D, double lr, double b1, double b2, float eps,
-                                                      const int64_t* __restrict__ steps_done,
+                                                      int64_t* __restrict__ steps_done,
                                                       const float* __restrict__ tail, double* __restrict__ loss_out) {
-    const double t = (double)(*steps_done + 1);
+    const double t = (double)(steps_done[0] + 1);
     const double numel = ((double)tail[2] * 4096.0 + (double)tail[3]) * (double)D;
     const float gscale = (float)(2.0 / numel);
     AdamScalars a;
@@ -531,6 +531,14 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(float* __restrict__ W, flo
         float mi = m[i], vi = v[i], wi = W[i];
         adam_update(a, g[i] * gscale, mi, vi, wi);
         W[i] = wi; m[i] = mi; v[i] = vi;
+    }
+    // the last block to finish advances the step count (every block read it when it started): steps_done[1] is the
+    // arrival counter, left at zero again
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(steps_done + 1), 1ull);
+        if (old == (unsigned long long)gridDim.x - 1ull) { steps_done[1] = 0; steps_done[0] += 1; }
     }
 }
 
@@ -771,8 +779,7 @@ int som_adam_dp_f32(float* W, float* m, float* v, const float* g, int64_t n, int
         int blocks = grid_for(n, 256 * 4, 8);
         adam_dp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, m, v, g, n, D, lr, b1, b2, (float)eps, steps_done,
                                                                 tail, loss_out);
-        int rc = check_launch("adam_dp_kernel");
-        if (rc) return rc;
+        return check_launch("adam_dp_kernel");
     }
     step_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(steps_done);
     return check_launch("step_bump_kernel");

@@ -163,11 +163,11 @@ __global__ void __launch_bounds__(THREADS) adam_slice_bcast_kernel(const float4*
                                                                    float4* __restrict__ m, float4* __restrict__ v,
                                                                    const float4* __restrict__ g, int64_t n4, int D,
                                                                    double lr, double b1, double b2, float eps,
-                                                                   const int64_t* __restrict__ steps_done,
+                                                                   int64_t* __restrict__ steps_done,
                                                                    const float* __restrict__ tail,
                                                                    double* __restrict__ loss_out, Pads pads, int channel,
                                                                    int rank, int world) {
-    const double t = (double)(*steps_done + 1);
+    const double t = (double)(steps_done[0] + 1);
     const double numel = ((double)tail[2] * 4096.0 + (double)tail[3]) * (double)D;
     const float gs = (float)(2.0 / numel);
     AdamScalars a;
@@ -188,9 +188,13 @@ __global__ void __launch_bounds__(THREADS) adam_slice_bcast_kernel(const float4*
         mm_st(mc_W + 4 * q, wq);
     }
     __syncthreads();
+    if (threadIdx.x == 0) {                  // last block to arrive advances the step count (steps_done[1]: arrival counter)
+        __threadfence();
+        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(steps_done + 1), 1ull);
+        if (old == (unsigned long long)gridDim.x - 1ull) { steps_done[1] = 0; steps_done[0] += 1; }
+    }
     sync_blocks<true, true>(pads, channel, rank, world);
 }
-__global__ void step_bump_kernel(int64_t* steps_done) { *steps_done += 1; }
 
 static int make_pads(Pads* pads, void* const* signal_pads, int rank, int world) {
     SOM_REQUIRE(signal_pads != nullptr && world >= 2 && world <= MAX_WORLD && rank >= 0 && rank < world, SOM_E_BADARG,
@@ -292,8 +296,5 @@ extern "C" int som_peer_adam_slice_f32(const float* W_rows, void* mc_W_rows, flo
     adam_slice_bcast_kernel<<<grid_for(max_n / 4), THREADS, 0, (cudaStream_t)stream>>>(
         (const float4*)W_rows, (float*)mc_W_rows, (float4*)m_rows, (float4*)v_rows, (const float4*)g_rows, n / 4, D, lr, b1,
         b2, (float)eps, steps_done, tail, loss_out, pads, channel, rank, world);
-    rc = check_launch("peer_adam_slice_bcast_kernel");
-    if (rc) return rc;
-    peer::step_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(steps_done);
-    return check_launch("step_bump_kernel");
+    return check_launch("peer_adam_slice_bcast_kernel");
 }

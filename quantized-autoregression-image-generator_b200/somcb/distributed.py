@@ -10,9 +10,11 @@ Two shardings:
   in a CUDA graph (``use_cuda_graph``).
   BMU-only / histogram workloads need no exchange beyond a final all-reduce of K int64 counts.
 * unit-sharded search (``sharded_bmu``): rank r owns units [lo_r, hi_r); patches are replicated;
-  each rank returns (reduced distance, global index) candidates from the SAME kernel arithmetic as
-  the unsharded path, one all-gather of 12 B/patch/rank, then som_merge_candidates (smaller
-  distance, tie -> smaller global index == the single-device first-minimum rule).
+  each rank returns (reduced distance, global index) candidates from the same kernels as the
+  unsharded path, ONE all-gather of a packed 12 B/patch/rank record block, then som_merge_candidates
+  (smaller distance, tie -> smaller global index == the single-device first-minimum rule).  The
+  kernel plan (split arithmetic, unit / feature splits) depends on the shard's shape, so picks may
+  differ from the unsharded search between candidates closer than the 1e-6 near-tie rule.
 
 ``ops`` is injectable so the host logic (sharding arithmetic, collective wiring) is testable
 under gloo on CPU with a test double; the default is the CUDA library, which raises on CPU.
@@ -215,10 +217,14 @@ def sharded_bmu(x, geom, weight_shard, unit_offset, group=None, ops=None, c_norm
     if world == 1:
         return idx
     n = idx.numel()
-    all_rd = torch.empty(world * n, dtype=rd.dtype, device=rd.device)
-    all_idx = torch.empty(world * n, dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(all_rd, rd, group=group)      # rank-major: row r = rank r
-    dist.all_gather_into_tensor(all_idx, idx, group=group)
+    # ONE all-gather of a packed 12-byte-per-patch record block [idx (n int64) | rd (n fp32)] per rank
+    send = torch.empty(3 * n, dtype=torch.int32, device=idx.device)
+    send[:2 * n].view(torch.int64).copy_(idx)
+    send[2 * n:].view(torch.float32).copy_(rd)
+    recv = torch.empty(world, 3 * n, dtype=torch.int32, device=idx.device)
+    dist.all_gather_into_tensor(recv, send, group=group)      # rank-major: row r = rank r
+    all_idx = recv[:, :2 * n].contiguous().view(torch.int64)
+    all_rd = recv[:, 2 * n:].contiguous().view(torch.float32)
     merged, _ = ops.merge_candidates(all_rd.view(world, n), all_idx.view(world, n))
     return merged
 

@@ -225,11 +225,14 @@ def accumulate_packed(x, geom, bmu_idx, table, num_units, packed=None, ws=None):
 
 def adam_step_dp(weight, m, v, grad, dim, lr, steps_done, tail, loss_out=None, betas=(0.5, 0.999), eps=1e-8):
     """K4, data-parallel tail: ``grad`` unscaled (T @ Rbar_global), ``tail`` the all-reduced 4-float tail of
-    ``accumulate_packed``; scales by 2 / numel on the device, writes the loss, increments ``steps_done``."""
+    ``accumulate_packed``; scales by 2 / numel on the device, writes the loss, increments ``steps_done[0]``
+    (``steps_done``: two int64, [completed steps, scratch word kept at zero])."""
     lib = _lib.load()
     for t, nm in ((weight, "weight"), (m, "m"), (v, "v"), (grad, "grad"), (tail, "tail")):
         _req(t, torch.float32, nm)
     _req(steps_done, torch.int64, "steps_done")
+    if steps_done.numel() < 2:
+        raise ValueError("steps_done must hold two int64: [completed steps, scratch]")
     if loss_out is None:
         loss_out = torch.empty(1, dtype=torch.float64, device=weight.device)
     _req(loss_out, torch.float64, "loss_out")
@@ -374,6 +377,8 @@ def peer_adam_slice(w_rows, mc_w_rows, m_rows, v_rows, g_rows, max_n, dim, lr, s
     for t, nm in ((w_rows, "w_rows"), (m_rows, "m_rows"), (v_rows, "v_rows"), (g_rows, "g_rows"), (tail, "tail")):
         _req(t, torch.float32, nm)
     _req(steps_done, torch.int64, "steps_done")
+    if steps_done.numel() < 2:
+        raise ValueError("steps_done must hold two int64: [completed steps, scratch]")
     if loss_out is None:
         loss_out = torch.empty(1, dtype=torch.float64, device=w_rows.device)
     with torch.cuda.device(w_rows.device):

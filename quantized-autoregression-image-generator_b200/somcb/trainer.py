@@ -57,8 +57,8 @@ class SomTrainer:
         self.m = torch.zeros_like(w, requires_grad=False)
         self.v = torch.zeros_like(w, requires_grad=False)
         self.t = 0
-        # Adam's step count lives on the device (the captured graph and the eager path share it)
-        self.t_dev = torch.zeros(1, dtype=torch.int64, device=w.device)
+        # Adam's step count lives on the device (the captured graph and the eager path share it): [count, scratch]
+        self.t_dev = torch.zeros(2, dtype=torch.int64, device=w.device)
         self.packed = torch.empty(w.numel() + 4, dtype=torch.float32, device=w.device)
         self.last_bmu = None
         self.use_cuda_graph = bool(use_cuda_graph)
@@ -68,7 +68,9 @@ class SomTrainer:
     @torch.no_grad()
     def step(self, feature_map, bmu=None):
         """One training step on a (local) batch; returns the loss as a 0-dim float64 device
-        tensor (global mean squared error, as F.mse_loss over the global batch)."""
+        tensor (global mean squared error, as F.mse_loss over the global batch).  Under ``use_cuda_graph`` the
+        tensor is the captured graph's own output buffer: read it (``float(loss)``, ``.clone()``) before the same
+        graph is replayed again."""
         if self.use_cuda_graph and bmu is None and self.t >= 1 and feature_map.is_cuda:
             loss = self._graph_step(feature_map)
         else:
@@ -103,7 +105,8 @@ class SomTrainer:
         cb._norm_cache = None
         self.last_bmu = None
         self._bookkeeping()
-        return loss_static.clone().reshape(())
+        # the graph's own loss buffer (overwritten by the next replay of THIS graph): no copy kernel per step
+        return loss_static.reshape(())
 
     def _bookkeeping(self):
         # schedule bookkeeping, in the reference's order (train_codebook.py:247-249, 300-304)

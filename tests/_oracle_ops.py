@@ -100,9 +100,9 @@ def accumulate_packed(x, geom, bmu_idx, table, num_units, packed=None, ws=None):
 
 def adam_step_dp(weight, m, v, grad, dim, lr, steps_done, tail, loss_out=None, betas=(0.5, 0.999), eps=1e-8):
     numel = (float(tail[2]) * 4096.0 + float(tail[3])) * dim
-    step = int(steps_done) + 1
+    step = int(steps_done[0]) + 1
     adam_step(weight, m, v, grad * torch.tensor(2.0 / numel, dtype=torch.float32), lr, step, betas, eps)
-    steps_done += 1
+    steps_done[0] += 1
     loss = ((tail[0].double() + tail[1].double()) / numel).reshape(1)
     if loss_out is not None:
         loss_out.copy_(loss)

@@ -299,7 +299,7 @@ def test_cuda_graph_trainer_matches_eager_trainer():
         assert abs(l0 - l1) <= 1e-6 * abs(l0), f"step {step}: loss {l0} vs {l1}"
         assert abs(l0 - l2) <= 1e-6 * abs(l0), f"step {step}: loss {l0} vs {l2} (alias)"
     for tr in trainers[1:]:
-        assert len(tr._graphs) == 3 and tr.t == 60 and int(tr.t_dev) == 60
+        assert len(tr._graphs) == 3 and tr.t == 60 and int(tr.t_dev[0]) == 60
         assert trainers[0].cb.neighbourhood_range == tr.cb.neighbourhood_range == k // 2 - 3
         assert_close_norm(tr.cb.codebook.weight.data, trainers[0].cb.codebook.weight.data,
                           what="weights after 60 graph-replayed steps")
@@ -310,7 +310,7 @@ def test_cuda_graph_trainer_matches_eager_trainer():
     for tr in trainers[:2]:
         tr.step(x, bmu=forced)
         tr.step(x)
-    assert trainers[1].t == 62 and int(trainers[1].t_dev) == 62
+    assert trainers[1].t == 62 and int(trainers[1].t_dev[0]) == 62
     assert_close_norm(trainers[1].cb.codebook.weight.data, trainers[0].cb.codebook.weight.data,
                       what="weights after an eager step between graph replays")
 
@@ -350,14 +350,14 @@ def test_packed_accumulate_and_device_scaled_adam_match_the_host_scaled_path():
     numel = x.numel()
     w_a, m_a, v_a = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
     w_b, m_b, v_b = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
-    t_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+    t_dev = torch.zeros(2, dtype=torch.int64, device=DEV)
     for t in (1, 2, 3):
         g_a = ops.neighbourhood_filter(rbar, 300, scale=2.0 / numel)
         ops.adam_step(w_a, m_a, v_a, g_a, 1e-4, t)
         g_b = ops.neighbourhood_filter(rbar, 300, scale=1.0)
         loss = ops.adam_step_dp(w_b, m_b, v_b, g_b, d, 1e-4, t_dev, packed[k * d:])
         assert torch.equal(w_a, w_b) and torch.equal(v_a, v_b)
-    assert int(t_dev) == 3
+    assert int(t_dev[0]) == 3 and int(t_dev[1]) == 0
     assert abs(float(loss) - float(sse) / numel) <= 1e-12 * float(loss)
 
 

@@ -42,7 +42,7 @@ packed = torch.empty(k * d + 4, dtype=torch.float32, device=dev)
 ops.accumulate_packed(x, geom, bmu, wt, k, packed=packed)
 grad = ops.neighbourhood_filter(packed[:k * d].view(k, d), rng)
 wc, mc, vc = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
-tdev = torch.ones(1, dtype=torch.int64, device=dev)
+tdev = torch.tensor([1, 0], dtype=torch.int64, device=dev)
 lo = torch.empty(1, dtype=torch.float64, device=dev)
 parts = {"filter_W": lambda: ops.neighbourhood_filter(w, rng), "norms": lambda: ops.prepare_codebook(w),
          "bmu": lambda: ops.bmu(x, geom, w, cn), "bmu_tf32": lambda: ops.bmu(x, geom, w, cn, variant=ops.SOM_BMU_TC_TF32),
