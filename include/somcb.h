@@ -205,6 +205,21 @@ SOM_API int som_adam_dp_f32(float* W, float* m, float* v, const float* g, int64_
                     double lr, double b1, double b2, double eps, int64_t* steps_done,
                     const float* tail, double* loss_out, void* stream);
 
+/* ---- one-kernel training step for small problems (BASELINE config 1: 512 patches, K = 1024, D = 64) --------
+ * The whole iteration of train_codebook.py:225-249 (forward with the Gaussian neighbourhood, mse_loss, backward,
+ * Adam(b1, b2, eps); models/Codebook.py:77-135) as ONE cooperative kernel with three grid barriers: W~ = T @ W,
+ * BMU (fp32 FFMA, first minimum on ties), per-unit residual sums in ascending patch order, G = (2/numel) T @ Rbar,
+ * Adam in place on W / m / v, loss = mean squared error to loss_out (device double, may be NULL), BMU indices to
+ * bmu_out (n_patches int64, may be NULL).  Covered shapes: n_patches <= 2048, D in {16, 32, 64, 128, 256},
+ * K <= 32 * SMs, <= 16 * SMs patches, band half-width <= 2048: som_step_small_workspace_bytes returns 0 otherwise
+ * (and the call SOM_E_UNSUPPORTED) -- use the separate kernels then.  steps_done: two int64 as for som_adam_dp_f32
+ * ([0] is read as the completed-step count and incremented; [1] is not touched).                              */
+SOM_API size_t som_step_small_workspace_bytes(int64_t n_patches, int D, int K, double neighbourhood_range);
+SOM_API int som_step_small_f32(const float* x, int64_t n_img, int C, int H, int Wd, int pH, int pW,
+                       float* W, float* m, float* v, int K, double neighbourhood_range,
+                       double lr, double b1, double b2, double eps, int64_t* steps_done,
+                       int64_t* bmu_out, double* loss_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- data-parallel tail over NVLink / NVSwitch peer memory (new; multi-GPU only) -------------------------
  * Replaces, across ranks, "all-reduce the accumulators, then every rank filters and updates the whole codebook"
  * (train_codebook.py:240-242 + models/Codebook.py:112-130 have no multi-GPU form in the reference).  Pointers

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "somcb", "libsomcb.so")
 OBJ_DIR = os.path.join(HERE, "build")
 SOURCES = ["som_core.cu", "som_filter.cu", "som_filter_tc.cu", "som_accumulate.cu", "som_bmu_ffma.cu", "som_bmu_tc.cu",
-           "som_bmu_tc_s.cu", "som_bmu_tc_l.cu", "som_bmu_tc_l16.cu", "som_bmu.cu", "som_peer.cu"]
+           "som_bmu_tc_s.cu", "som_bmu_tc_l.cu", "som_bmu_tc_l16.cu", "som_bmu.cu", "som_peer.cu", "som_step_small.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",

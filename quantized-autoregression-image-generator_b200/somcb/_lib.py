@@ -48,6 +48,10 @@ SIGNATURES = {
                                                c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "som_adam_dp_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double,
                                 c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "som_step_small_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_double]),
+    "som_step_small_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_size_t, c_void_p]),
     "som_peer_signal_bytes": (c_size_t, []),
     "som_peer_allreduce_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "som_peer_reduce_rows_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

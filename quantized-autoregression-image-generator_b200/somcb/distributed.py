@@ -221,8 +221,9 @@ def sharded_bmu(x, geom, weight_shard, unit_offset, group=None, ops=None, c_norm
     send = torch.empty(3 * n, dtype=torch.int32, device=idx.device)
     send[:2 * n].view(torch.int64).copy_(idx)
     send[2 * n:].view(torch.float32).copy_(rd)
-    recv = torch.empty(world, 3 * n, dtype=torch.int32, device=idx.device)
+    recv = torch.empty(world * 3 * n, dtype=torch.int32, device=idx.device)
     dist.all_gather_into_tensor(recv, send, group=group)      # rank-major: row r = rank r
+    recv = recv.view(world, 3 * n)
     all_idx = recv[:, :2 * n].contiguous().view(torch.int64)
     all_rd = recv[:, 2 * n:].contiguous().view(torch.float32)
     merged, _ = ops.merge_candidates(all_rd.view(world, n), all_idx.view(world, n))

@@ -288,6 +288,34 @@ def adam_step_dev(weight, m, v, grad, lr, steps_done, betas=(0.5, 0.999), eps=1e
     return weight
 
 
+def step_small_supported(geom, num_units, neighbourhood_range):
+    """Whether the one-kernel training step covers this shape (include/somcb.h, som_step_small_f32)."""
+    return _lib.load().som_step_small_workspace_bytes(n_patches_of(geom), dim_of(geom), int(num_units),
+                                                      float(neighbourhood_range)) > 0
+
+
+def step_small(x, geom, weight, m, v, neighbourhood_range, lr, steps_done, betas=(0.5, 0.999), eps=1e-8,
+               want_bmu=True, loss_out=None):
+    """The whole training step in one cooperative kernel (small problems).  Returns (loss (1,) float64, bmu or None)."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    for t, nm in ((weight, "weight"), (m, "m"), (v, "v")):
+        _req(t, torch.float32, nm)
+    _req(steps_done, torch.int64, "steps_done")
+    k, d = weight.shape
+    npat = n_patches_of(geom)
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float64, device=x.device)
+    bmu_out = torch.empty(npat, dtype=torch.int64, device=x.device) if want_bmu else None
+    with torch.cuda.device(x.device):
+        ws, ws_bytes = _workspace(lib.som_step_small_workspace_bytes(npat, d, k, float(neighbourhood_range)), x.device)
+        check("som_step_small_f32",
+              lib.som_step_small_f32(_ptr(x), *geom, _ptr(weight), _ptr(m), _ptr(v), k, float(neighbourhood_range),
+                                     float(lr), float(betas[0]), float(betas[1]), float(eps), _ptr(steps_done),
+                                     _ptr(bmu_out), _ptr(loss_out), _ptr(ws), ws_bytes, _stream(x)))
+    return loss_out, bmu_out
+
+
 def gather_rows(weight, keep):
     lib = _lib.load()
     w = _req(weight, torch.float32, "weight")

@@ -27,7 +27,7 @@ class SomTrainer:
 
     def __init__(self, codebook, lr, neighbourhood_step, lr_step=100000, global_steps=0,
                  betas=(0.5, 0.999), eps=1e-8, ops=None, reduce_fn=None, world_size=1,
-                 use_cuda_graph=False, check_nan=False):
+                 use_cuda_graph=False, check_nan=False, small_step_kernel=True):
         """``codebook``: a somcb.Codebook on a CUDA device.  ``reduce_fn(packed)`` sums the packed
         accumulator buffer in place across data-parallel ranks (None: single device).
 
@@ -52,6 +52,7 @@ class SomTrainer:
         self.reduce_fn = reduce_fn
         self.world_size = int(world_size)
         self.check_nan = bool(check_nan)
+        self.small_step_kernel = bool(small_step_kernel)    # False: always the separate kernels (tests, A/B)
         w = codebook.codebook.weight
         # the reference does not checkpoint Adam state: a resume restarts the moments at zero
         self.m = torch.zeros_like(w, requires_grad=False)
@@ -132,6 +133,15 @@ class SomTrainer:
         k, d = cb.num_embeddings, cb.embedding_dim
         rng = cb.neighbourhood_range
         kd = k * d
+
+        if (bmu is None and self.reduce_fn is None and self.small_step_kernel and cb.bmu_variant == ops.SOM_BMU_AUTO
+                and getattr(ops, "step_small_supported", None) is not None and ops.step_small_supported(geom, k, rng)):
+            # small problems (BASELINE config 1): the whole step is ONE cooperative kernel, a launch costs more than
+            # any of the step's kernels at this size
+            loss, self.last_bmu = ops.step_small(x, geom, w, self.m, self.v, rng, self.lr, self.t_dev,
+                                                 betas=self.betas, eps=self.eps)
+            cb._norm_cache = None
+            return loss
 
         wt = ops.neighbourhood_filter(w, rng)
         x_acc, geom_acc = x, geom

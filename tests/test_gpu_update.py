@@ -386,3 +386,39 @@ def test_staging_copy_from_the_bmu_kernel_feeds_the_accumulation():
         xs = synthetic_fmaps(8, 1).to(DEV)
         g8 = ops.geometry(xs.shape, (4, 4))
         ops.bmu(xs, g8, trained_like_codebook(1024, (4, 4), 7).to(DEV), stage=torch.empty(512, 64, device=DEV))
+
+
+@pytest.mark.parametrize("p,k,n_f,rng", [(4, 1024, 8, 512), (2, 512, 4, 256), (8, 300, 16, 32), (4, 4096, 8, 512),
+                                         (4, 1024, 32, 100)])
+def test_one_kernel_small_step_matches_the_separate_kernels(p, k, n_f, rng):
+    """som_step_small_f32 (BASELINE config 1's whole step as one cooperative kernel) against the step built from the
+    separate kernels: 12 free-running steps with the neighbourhood range shrinking, same losses, weights and BMUs; also
+    captured in a CUDA graph."""
+    from oracle.step_oracle import synthetic_fmaps, trained_like_codebook
+    pd = (p, p)
+    w0 = trained_like_codebook(k, pd, 7)
+    trainers = []
+    for small, graph in ((True, False), (False, False), (True, True)):
+        cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                            init_neighbour_range=rng)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(w0)
+        trainers.append(somcb.SomTrainer(cb.to(DEV), lr=1e-4, neighbourhood_step=5, small_step_kernel=small,
+                                         use_cuda_graph=graph))
+    geom = ops.geometry((n_f, 4, 32, 32), pd)
+    assert ops.step_small_supported(geom, k, rng)
+    for step in range(12):
+        x = synthetic_fmaps(n_f, 700 + step).to(DEV)
+        ls = [float(tr.step(x)) for tr in trainers]
+        assert abs(ls[0] - ls[1]) <= 2e-6 * abs(ls[1]), f"step {step}: loss {ls[0]} vs {ls[1]}"
+        assert ls[0] == ls[2], f"step {step}: graph replay {ls[2]} vs eager {ls[0]}"
+        if step == 0:
+            flat = flat_patches(x.cpu(), pd)
+            assert_bmu_parity(trainers[0].last_bmu, trainers[1].last_bmu, flat, w0)
+    assert trainers[0].t == 12 and int(trainers[0].t_dev[0]) == 12
+    assert_close_norm(trainers[0].cb.codebook.weight.data, trainers[1].cb.codebook.weight.data, 1e-6,
+                      "one-kernel step vs separate kernels")
+    assert torch.equal(trainers[0].cb.codebook.weight.data, trainers[2].cb.codebook.weight.data)
+    # not covered: more than 2048 patches, or a band whose staged rows do not fit in shared memory
+    assert not ops.step_small_supported(ops.geometry((64, 4, 32, 32), (2, 2)), 512, 256)
+    assert not ops.step_small_supported(ops.geometry((8, 4, 32, 32), (8, 8)), 300, 150)
