@@ -674,6 +674,9 @@ static void make_plan(Plan* pl, int64_t n, int D, int K) {
     int S = sm_count() / pl->n_mtiles;
     if (S > pl->DB / 8) S = pl->DB / 8;
     if (S > MAX_SPLIT) S = MAX_SPLIT;
+    // the S x N x K partial-distance buffer is written and re-read through HBM on every call: keep it within 256 MB
+    // (K = 32 768, D = 512, 9.4k patches would otherwise take 2.5 GB); beyond that the unit-split / streamed modes apply
+    while (S > 1 && (size_t)S * pl->n_mtiles * TM * (size_t)pl->K_pad * 4 > ((size_t)256 << 20)) --S;
     if (S < 1) S = 1;
     pl->fb_per_split = (pl->DB + S - 1) / S;
     pl->S = (pl->DB + pl->fb_per_split - 1) / pl->fb_per_split;

@@ -41,6 +41,8 @@ struct Params {
     int K, D, h, nkb;
     float two_var, scale;
     float* out;
+    int ks;                 // k-split: CTA blockIdx.z takes the k-blocks kb = z (mod ks); ks is 1 or NACC
+    float* partial;         // ks > 1: [ks][K][D] unscaled partial sums, added by filter_reduce_kernel
 };
 
 struct __align__(8) Barriers {
@@ -109,6 +111,10 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ut = blockIdx.x, ct = blockIdx.y;
+    // k-split (few tiles, e.g. a data-parallel rank's slice of units): the NACC round-robin accumulators of the unsplit
+    // kernel become NACC CTAs -- CTA z runs exactly the accumulation chain of accumulator z, and filter_reduce_kernel
+    // adds the partial tiles in the same fixed order, so the result is bit-identical to the unsplit kernel's
+    const int ksp = (int)blockIdx.z, KS = P.ks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.full[s], 1 + BUILD_WARPS); mbar_init(&bars.empty[s], 1); }
@@ -144,7 +150,7 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = ksp; kb < nkb; kb += KS) {
                 mbar_wait(&bars.empty[stage], phase ^ 1);
                 uint8_t* sb = ring + (size_t)stage * STAGE + 2 * A_BLK_BYTES;
                 mbar_expect_tx(&bars.full[stage], 2 * B_BYTES);
@@ -159,7 +165,7 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
         const bool leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = ksp; kb < nkb; kb += KS) {
             mbar_wait(&bars.full[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE);
@@ -168,7 +174,7 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
             // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of
             // the accumulation chain (measured 1.7e-6 relative after 372 MMAs into one accumulator, band 851): the
             // k-blocks are dealt round-robin to NACC accumulators and the epilogue adds those in fp32 (4e-7).
-            const uint32_t d_addr = tmem_base + (uint32_t)(kb % NACC) * TNF;
+            const uint32_t d_addr = tmem_base + (KS > 1 ? 0u : (uint32_t)(kb % NACC) * TNF);
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < KBLK / 8; ++ks) {
@@ -177,7 +183,7 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
                     mma_tf32_n<TNF>(d_addr, ahi + 2u * ks, blo + 2u * ks, 1u);
                 }
                 tc_commit(&bars.empty[stage]);
-                if (kb == nkb - 1) tc_commit(&bars.acc_full);
+                if (kb + KS >= nkb) tc_commit(&bars.acc_full);
             }
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
@@ -191,7 +197,7 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
             const uint32_t sw = (uint32_t)(ul & 7);
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = ksp; kb < nkb; kb += KS) {
                 mbar_wait_warp<false>(&bars.empty[stage], phase ^ 1, lane);
                 uint8_t* sa = ring + (size_t)stage * STAGE + row_off;
                 // A[ul][jl] = w(jl - h - ul), jl = 32 kb + c: consecutive rows read consecutive table entries
@@ -219,19 +225,22 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
         const int u = ut * TMU + lg * 32 + lane;
         const bool row_ok = u < P.K;
         const bool v4 = ((P.D & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
-        float* orow = P.out + (int64_t)(row_ok ? u : 0) * P.D;
+        float* orow = (KS > 1 ? P.partial + (int64_t)ksp * P.K * P.D : P.out) + (int64_t)(row_ok ? u : 0) * P.D;
+        const float oscale = KS > 1 ? 1.0f : P.scale;            // split: raw partial sums, scaled after the reduction
 #pragma unroll 1
         for (int c = 0; c < TNF / 32; ++c) {
             uint32_t v[32], w[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32);
             tmem_ld32_issue(taddr, v);
             tmem_ld_wait(v);
+            if (KS == 1) {
 #pragma unroll
-            for (int a = 1; a < NACC; ++a) {                     // fixed order: ((a0 + a1) + a2) + a3
-                tmem_ld32_issue(taddr + (uint32_t)(a * TNF), w);
-                tmem_ld_wait(w);
+                for (int a = 1; a < NACC; ++a) {                 // fixed order: ((a0 + a1) + a2) + a3
+                    tmem_ld32_issue(taddr + (uint32_t)(a * TNF), w);
+                    tmem_ld_wait(w);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+                }
             }
             const int d0 = ct * TNF + c * 32;
             if (row_ok && d0 < P.D) {
@@ -239,12 +248,12 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         *reinterpret_cast<float4*>(orow + d0 + 4 * q) =
-                            make_float4(P.scale * __uint_as_float(v[4 * q]), P.scale * __uint_as_float(v[4 * q + 1]),
-                                        P.scale * __uint_as_float(v[4 * q + 2]), P.scale * __uint_as_float(v[4 * q + 3]));
+                            make_float4(oscale * __uint_as_float(v[4 * q]), oscale * __uint_as_float(v[4 * q + 1]),
+                                        oscale * __uint_as_float(v[4 * q + 2]), oscale * __uint_as_float(v[4 * q + 3]));
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (d0 + i < P.D) orow[d0 + i] = P.scale * __uint_as_float(v[i]);
+                        if (d0 + i < P.D) orow[d0 + i] = oscale * __uint_as_float(v[i]);
                 }
             }
         }
@@ -259,9 +268,21 @@ done:
     }
 }
 
+// out = scale * (((p0 + p1) + p2) + p3): the unsplit epilogue's order
+__global__ void __launch_bounds__(256) filter_reduce_kernel(const float* __restrict__ partial, int64_t n, float scale,
+                                                            float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v = partial[i];
+#pragma unroll
+        for (int a = 1; a < NACC; ++a) v += partial[(int64_t)a * n + i];
+        out[i] = scale * v;
+    }
+}
+
 struct Plan {
-    int h, L, nkb, Kp, tnf;
-    size_t off_hi, off_lo, total;
+    int h, L, nkb, Kp, tnf, ks;
+    size_t off_hi, off_lo, off_part, total;
 };
 
 static void make_plan(Plan* pl, int K, int D, int h) {
@@ -274,7 +295,11 @@ static void make_plan(Plan* pl, int K, int D, int h) {
     const size_t one = align_up((size_t)D * pl->Kp * sizeof(float), 1024);
     pl->off_hi = 0;
     pl->off_lo = one;
-    pl->total = 2 * one;
+    // static rule: with fewer tiles than half the SMs, the NACC accumulation chains of a tile go to NACC CTAs
+    const int64_t tiles = (int64_t)n_ut * ((D + pl->tnf - 1) / pl->tnf);
+    pl->ks = (tiles * 2 <= sm_count()) ? NACC : 1;
+    pl->off_part = 2 * one;
+    pl->total = 2 * one + (pl->ks > 1 ? align_up((size_t)pl->ks * K * D * sizeof(float), 1024) : 0);
 }
 
 }  // namespace ftc
@@ -286,8 +311,9 @@ int filter_band_half_width(float two_var, int K);
 bool filter_tc_applicable(int K, int D, int h) {
     // ... and one CTA per tile: with fewer than 32 tiles most SMs idle and the FFMA kernel (32-unit tiles) is faster
     // (measured at C1, K = 1024, D = 64: 8 tiles, 28 us against 21 us)
+    // (fewer than 74 tiles are k-split over 4 CTAs each; below ~12 tiles the FFMA kernel wins again)
     const int64_t tiles = ceil_div64(K, ftc::TMU) * ceil_div64(D, D > 64 ? 128 : 64);
-    if (K < 256 || D < 48 || h > ftc::MAX_H || tiles < 32) return false;
+    if (K < 256 || D < 48 || h > ftc::MAX_H || tiles < 12) return false;
     static int cc_major = -1;
     if (cc_major < 0) {
         int dev = 0, v = 0;
@@ -330,6 +356,7 @@ int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, i
     if (rc) return rc;
     Params P;
     P.K = K; P.D = D; P.h = h; P.nkb = pl.nkb; P.two_var = two_var; P.scale = scale; P.out = out;
+    P.ks = pl.ks; P.partial = (float*)((char*)ws + pl.off_part);
     const size_t smem = smem_bytes(pl.tnf, h);
     static PerDeviceFlag attr_done;
     if (attr_done.pending()) {
@@ -339,10 +366,16 @@ int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, i
         if (e != cudaSuccess) { set_error("filter(tc): smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done.set();
     }
-    dim3 grid((unsigned)ceil_div64(K, TMU), (unsigned)ceil_div64(D, pl.tnf));
+    dim3 grid((unsigned)ceil_div64(K, TMU), (unsigned)ceil_div64(D, pl.tnf), (unsigned)pl.ks);
     if (pl.tnf == 128) filter_tc_kernel<128><<<grid, NUM_THREADS, smem, st>>>(map_bhi, map_blo, P);
     else filter_tc_kernel<64><<<grid, NUM_THREADS, smem, st>>>(map_bhi, map_blo, P);
-    return check_launch("filter_tc_kernel");
+    rc = check_launch("filter_tc_kernel");
+    if (rc || pl.ks == 1) return rc;
+    const int64_t n = (int64_t)K * D;
+    int blocks = (int)ceil_div64(n, 256 * 4);
+    if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+    filter_reduce_kernel<<<blocks, 256, 0, st>>>(P.partial, n, scale, out);
+    return check_launch("filter_reduce_kernel");
 }
 
 }  // namespace som
