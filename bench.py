@@ -230,10 +230,10 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # headline: the C4 step, strong-scaled
 # ---------------------------------------------------------------------------------------------------------------
-def _make_trainer(cb, world, graph=True, tail="auto"):
+def _make_trainer(cb, world, graph=True, tail="auto", wt="full"):
     import somcb
     kw = dict(lr=C4["lr"], neighbourhood_step=C4["neighbourhood_step"], use_cuda_graph="alias" if graph else False)
-    return somcb.DataParallelSom(cb, tail=tail, **kw) if world > 1 else somcb.SomTrainer(cb, **kw)
+    return somcb.DataParallelSom(cb, tail=tail, wt=wt, **kw) if world > 1 else somcb.SomTrainer(cb, **kw)
 
 
 def run_headline(args, dev, world, rank, peaks):
@@ -249,7 +249,7 @@ def run_headline(args, dev, world, rank, peaks):
     # global batch b = fmaps of seed 5000 + b (generated per rank for its own contiguous share: seeds differ per rank)
     xs = [_fmaps(share, 5000 + 131 * b + rank, dev) for b in range(n_rot)]
     cb = _codebook(C4["K"], C4["patch"], dev)
-    tr = _make_trainer(cb, world, tail=args.tail)
+    tr = _make_trainer(cb, world, tail=args.tail, wt=args.wt)
     if world > 1:
         tr.broadcast_weights(0)
     tail_mode = getattr(tr, "tail", "single")
@@ -368,11 +368,13 @@ def run_headline(args, dev, world, rank, peaks):
             ops.peer_reduce_rows(mc["packed"], tr._peer_packed, k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1)
             gh = ops.neighbourhood_filter(rsum, rng)
             dist.barrier()
-            for name in ("filter_W", "filter_Rbar", "adam"):
+            for name in ("filter_Rbar", "adam"):
                 parts.pop(name)
-            parts["slice: filter_W rows"] = _timed(lambda: ops.neighbourhood_filter(w[g0:g1], rng), reps)
-            parts["slice: multicast W~ rows + barrier"] = _timed(
-                lambda: ops.peer_bcast_rows(wth[lo_u - g0:hi_u - g0], mc["wt"] + lo_u * d * 4, max_own * d, rk, world, sig, 0), reps)
+            if tr.wt_mode == "slice":
+                parts.pop("filter_W")
+                parts["slice: filter_W rows"] = _timed(lambda: ops.neighbourhood_filter(w[g0:g1], rng), reps)
+                parts["slice: multicast W~ rows + barrier"] = _timed(
+                    lambda: ops.peer_bcast_rows(wth[lo_u - g0:hi_u - g0], mc["wt"] + lo_u * d * 4, max_own * d, rk, world, sig, 0), reps)
             parts["slice: in-switch reduce of Rbar rows + halo"] = _timed(
                 lambda: ops.peer_reduce_rows(mc["packed"], tr._peer_packed, k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1), reps)
             parts["slice: filter_Rbar rows"] = _timed(lambda: ops.neighbourhood_filter(rsum, rng), reps)
@@ -386,7 +388,9 @@ def run_headline(args, dev, world, rank, peaks):
     breakdown["sum_of_parts_ms"] = ksum
     breakdown["graph_step_ms"] = ms_step
     breakdown["note"] = ("each op timed alone (eager, its own pre-pass launches included) on one rank's share, max "
-                         "over ranks; the step itself is one CUDA-graph replay")
+                         "over ranks; the step itself is one CUDA-graph replay.  Ops of a few microseconds are bound by "
+                         "the eager launch path here (a filter call: ~32 us eager, 15-32 us on the GPU): "
+                         "tools/graph_time.py has their GPU times from graph replay")
 
     # ---- roofline of the dominant kernel (BMU) --------------------------------------------------------------------
     n_local = share * C4["seq"]
@@ -594,6 +598,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 20)")
+    ap.add_argument("--wt", default="full", choices=["slice", "full"],
+                    help="peer tail: W~ = T @ W per slice + multicast, or the whole filter on every rank")
     ap.add_argument("--tail", default="auto", choices=["auto", "peer", "nccl"],
                     help="data-parallel tail: sharded over NVSwitch multicast peer memory, or NCCL all-reduce + replicated")
     args = ap.parse_args()

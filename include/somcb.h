@@ -226,17 +226,20 @@ SOM_API int som_step_small_f32(const float* x, int64_t n_img, int C, int H, int 
  * named mc_* are NVSwitch MULTICAST addresses of caller-owned symmetric allocations (the same offset in the same
  * allocation on every rank); `signal_pads` is a HOST array of `world` device pointers, entry r = rank r's flag
  * area (som_peer_signal_bytes() bytes, zero-filled once, peer-mapped) as seen from THIS rank.  Every call must be
- * made by all ranks in the same order with the same `channel` (0..3) and the same max_* arguments (the grids pair
- * up block by block across ranks); flags reset themselves, so the calls can be replayed from a CUDA graph.
- * A peer that never arrives makes the kernel trap after ~4 s instead of hanging.                               */
+ * made by all ranks in the same order with the same `channel` (0..3); the flags reset themselves, so the calls can
+ * be replayed from a CUDA graph (the max_* arguments are kept for ABI stability and ignored).  One barrier costs
+ * `world` remote atomics: the last block of a kernel to arrive runs the exchange for its grid, and a kernel that
+ * must see the peers' earlier work is preceded by a one-block barrier kernel.  A peer that never arrives makes the
+ * kernel trap after ~4 s instead of hanging.                                                                  */
 SOM_API size_t som_peer_signal_bytes(void);
 /* In-place all-reduce(sum) of n floats (n % 4 == 0): rank r reduces quads [r*n/4/world, ...) in the switch
  * (multimem.ld_reduce) and stores them to every rank (multimem.st).  With peer_bufs (HOST array of the buffer's
- * `world` peer addresses) and local_buf (this rank's own address) the buffer is a packed accumulator buffer:
- * its last 4 floats are the tail of som_accumulate_packed_nchw_f32 and are summed EXACTLY instead -- every rank
- * reads the R tails through the peer addresses, adds them in rank order (squared error in fp64) and writes the
- * result to its local tail (the in-switch fp32 adder is not exact enough for the loss).  Both NULL: plain data. */
-SOM_API int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer_bufs, float* local_buf, int rank,
+ * `world` peer addresses) and tail_out (a LOCAL 4-float buffer, 16-byte aligned, not part of the buffer) the buffer
+ * is a packed accumulator buffer: its last 4 floats are the tail of som_accumulate_packed_nchw_f32; they stay as
+ * they are on every rank and are summed EXACTLY into tail_out instead -- every rank reads the R tails through the
+ * peer addresses and adds them in rank order, the squared error in fp64 (the patch count must be exact).
+ * Both NULL: plain data, all n floats reduced in the switch.                                                  */
+SOM_API int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer_bufs, float* tail_out, int rank,
                            int world, void* const* signal_pads, int channel, void* stream);
 /* Rows [row0, row1) of the K x D accumulator matrix at mc_packed (layout of som_accumulate_packed_nchw_f32),
  * reduced over the ranks into LOCAL out_rows, and the reduced 4-float tail into LOCAL out_tail: the

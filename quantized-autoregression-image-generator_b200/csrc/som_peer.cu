@@ -16,10 +16,12 @@
 //   peer_allreduce     plain in-place all-reduce (ld_reduce + multimem.st of a 1/R slice per rank) for the case where
 //                      slicing does not pay (halo >= slice)
 //
-// Synchronisation between ranks is per CTA: block b of every rank signals block b of every peer through 32-bit
-// flags in peer memory (compare-and-swap 0 -> 1 by the sender, 1 -> 0 by the receiver, system scope), so the flags
-// reset themselves and the kernels can be replayed from a CUDA graph.  Every grid that synchronises has the same
-// size on all ranks.  Spins are bounded (~4 s): a missing peer traps instead of hanging the GPU.
+// Synchronisation between ranks: one 32-bit flag per (channel, sender) in every rank's peer-mapped flag area --
+// compare-and-swap 0 -> 1 by the sender, 1 -> 0 by the receiver, system scope, so the flags reset themselves and the
+// kernels replay from a CUDA graph.  A kernel that must publish its stores lets its LAST block (local arrival
+// counter) run the exchange for the whole grid; a kernel that must see the peers' earlier work is preceded by a
+// one-block barrier kernel.  `world` remote atomics per barrier (a first version synchronised every block with its peer
+// blocks: blocks x world NVLink atomics per kernel).  Spins are bounded (~4 s): a missing peer traps instead of hanging.
 // Buffers are caller-owned symmetric (peer-mapped + multicast) allocations; the library keeps no pointers.
 #include "som_common.cuh"
 
@@ -28,9 +30,8 @@ namespace peer {
 
 constexpr int MAX_WORLD = 16;
 constexpr int THREADS = 512;
-constexpr int MAX_BLOCKS = 64;
 
-struct Pads { uint32_t* p[MAX_WORLD]; };       // signal flags of every rank (peer-mapped addresses), [channel][block][rank]
+struct Pads { uint32_t* p[MAX_WORLD]; };       // flag area of every rank (peer-mapped addresses), layout at counter_of()
 
 __device__ __forceinline__ uint64_t gtimer() {
     uint64_t v;
@@ -45,18 +46,45 @@ __device__ __forceinline__ uint32_t cas_sys(uint32_t* addr, uint32_t cmp, uint32
     else asm volatile("atom.global.relaxed.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
     return old;
 }
-// Block b of this rank <-> block b of every peer.  PREV: this block's earlier writes must be visible to the peers'
-// blocks (release); NEXT: the peers' earlier writes must be visible to this block afterwards (acquire).
+// The cross-rank barrier of a whole GRID: the last block to arrive (local arrival counter, wraps to zero by itself) runs
+// the rank-to-rank signal exchange on behalf of all blocks, so a kernel costs `world` remote atomics instead of
+// blocks x world (measured at 8 ranks: the per-block form spent most of the tail's time in NVLink atomics).
+// Call after the block's global / multicast stores; `counter` is a zero-initialised word of this rank's flag area.
 template <bool PREV, bool NEXT>
-__device__ __forceinline__ void sync_blocks(const Pads& pads, int channel, int rank, int world) {
+__device__ __forceinline__ void grid_sync_ranks(const Pads& pads, uint32_t* counter, int channel, int rank, int world) {
+    __shared__ int is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                                  // this block's stores before the arrival
+        is_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        if ((int)threadIdx.x < world) {
+            __threadfence_system();
+            const int peer = threadIdx.x;
+            const uint64_t deadline = gtimer() + 4000000000ull;
+            uint32_t* put = pads.p[peer] + (size_t)channel * MAX_WORLD + rank;
+            while (cas_sys<PREV ? 1 : 0>(put, 0u, 1u) != 0u)
+                if (gtimer() > deadline) __trap();
+            uint32_t* get = pads.p[rank] + (size_t)channel * MAX_WORLD + peer;
+            while (cas_sys<NEXT ? 2 : 0>(get, 1u, 0u) != 1u)
+                if (gtimer() > deadline) __trap();
+        }
+    }
+}
+
+// one-block barrier over the ranks: everything this rank enqueued before it is visible to the peers' later kernels
+__global__ void __launch_bounds__(32) barrier_kernel(Pads pads, int channel, int rank, int world) {
     if ((int)threadIdx.x < world) {
+        __threadfence_system();
         const int peer = threadIdx.x;
         const uint64_t deadline = gtimer() + 4000000000ull;
-        uint32_t* put = pads.p[peer] + ((size_t)channel * MAX_BLOCKS + blockIdx.x) * MAX_WORLD + rank;
-        while (cas_sys<PREV ? 1 : 0>(put, 0u, 1u) != 0u)
+        uint32_t* put = pads.p[peer] + (size_t)channel * MAX_WORLD + rank;
+        while (cas_sys<1>(put, 0u, 1u) != 0u)
             if (gtimer() > deadline) __trap();
-        uint32_t* get = pads.p[rank] + ((size_t)channel * MAX_BLOCKS + blockIdx.x) * MAX_WORLD + peer;
-        while (cas_sys<NEXT ? 2 : 0>(get, 1u, 0u) != 1u)
+        uint32_t* get = pads.p[rank] + (size_t)channel * MAX_WORLD + peer;
+        while (cas_sys<2>(get, 1u, 0u) != 1u)
             if (gtimer() > deadline) __trap();
     }
 }
@@ -97,9 +125,8 @@ __device__ __forceinline__ float4 exact_tail(const Pads& bufs, int64_t q_tail, i
 // q_tail >= 0: that quad is the packed buffer's tail, excluded from the in-switch part and summed exactly
 __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q0, int64_t q1, int64_t q_tail,
                                                             float4* __restrict__ tail_out, Pads bufs, Pads pads,
-                                                            int channel, int rank, int world) {
-    sync_blocks<false, true>(pads, channel, rank, world);       // every rank's input is complete
-    __syncthreads();
+                                                            uint32_t* counter, int channel, int rank, int world) {
+    // (barrier_kernel ran before this launch: every rank's input is complete)
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q_tail >= 0 && blockIdx.x == 0 && threadIdx.x == 0) tail = exact_tail(bufs, q_tail, world);
     const int64_t stride = (int64_t)gridDim.x * THREADS;
@@ -112,8 +139,9 @@ __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q
         for (int u = 0; u < 4; ++u)
             if (q + u * stride < q1) mm_st(mc + 4 * (q + u * stride), v[u]);
     }
-    __syncthreads();
-    sync_blocks<true, true>(pads, channel, rank, world);        // every slice has landed everywhere (and every tail was read)
+    __threadfence_system();
+    grid_sync_ranks<true, true>(pads, counter, channel, rank, world);   // every slice has landed everywhere, every tail was read
+    // (the exact tail goes to a SEPARATE local buffer: peers may still be reading this rank's in-place tail)
     if (q_tail >= 0 && blockIdx.x == 0 && threadIdx.x == 0) *tail_out = tail;
 }
 
@@ -121,9 +149,8 @@ __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q
 // the ranks into local memory
 __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(const float* mc, int64_t q0, int64_t q1, int64_t q_tail,
                                                               float4* __restrict__ out, float4* __restrict__ tail_out,
-                                                              Pads bufs, Pads pads, int channel, int rank, int world) {
-    sync_blocks<false, true>(pads, channel, rank, world);       // every rank's accumulators are complete
-    __syncthreads();
+                                                              Pads bufs, int world) {
+    // (barrier_kernel ran before this launch: every rank's accumulators are complete)
     const int64_t stride = (int64_t)gridDim.x * THREADS;
     for (int64_t q = q0 + blockIdx.x * (int64_t)THREADS + threadIdx.x; q < q1; q += 4 * stride) {
         float4 v[4];
@@ -139,11 +166,11 @@ __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(const float* mc, i
 
 // local rows -> the same rows of every rank (multicast store), then the cross-rank barrier that makes them visible
 __global__ void __launch_bounds__(THREADS) bcast_rows_kernel(const float4* __restrict__ src, float* mc_dst, int64_t n4,
-                                                             Pads pads, int channel, int rank, int world) {
+                                                             Pads pads, uint32_t* counter, int channel, int rank, int world) {
     const int64_t stride = (int64_t)gridDim.x * THREADS;
     for (int64_t q = blockIdx.x * (int64_t)THREADS + threadIdx.x; q < n4; q += stride) mm_st(mc_dst + 4 * q, src[q]);
-    __syncthreads();
-    sync_blocks<true, true>(pads, channel, rank, world);
+    __threadfence_system();
+    grid_sync_ranks<true, true>(pads, counter, channel, rank, world);
 }
 
 struct AdamScalars { float w1, b2, one_m_b2, step_size, bc2_sqrt, eps; };
@@ -165,8 +192,8 @@ __global__ void __launch_bounds__(THREADS) adam_slice_bcast_kernel(const float4*
                                                                    double lr, double b1, double b2, float eps,
                                                                    int64_t* __restrict__ steps_done,
                                                                    const float* __restrict__ tail,
-                                                                   double* __restrict__ loss_out, Pads pads, int channel,
-                                                                   int rank, int world) {
+                                                                   double* __restrict__ loss_out, Pads pads,
+                                                                   uint32_t* counter, int channel, int rank, int world) {
     const double t = (double)(steps_done[0] + 1);
     const double numel = ((double)tail[2] * 4096.0 + (double)tail[3]) * (double)D;
     const float gs = (float)(2.0 / numel);
@@ -187,13 +214,14 @@ __global__ void __launch_bounds__(THREADS) adam_slice_bcast_kernel(const float4*
         m[q] = mq; v[q] = vq;
         mm_st(mc_W + 4 * q, wq);
     }
+    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {                  // last block to arrive advances the step count (steps_done[1]: arrival counter)
         __threadfence();
         const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(steps_done + 1), 1ull);
         if (old == (unsigned long long)gridDim.x - 1ull) { steps_done[1] = 0; steps_done[0] += 1; }
     }
-    sync_blocks<true, true>(pads, channel, rank, world);
+    grid_sync_ranks<true, true>(pads, counter, channel, rank, world);
 }
 
 static int make_pads(Pads* pads, void* const* signal_pads, int rank, int world) {
@@ -202,6 +230,13 @@ static int make_pads(Pads* pads, void* const* signal_pads, int rank, int world) 
     for (int r = 0; r < MAX_WORLD; ++r) pads->p[r] = r < world ? (uint32_t*)signal_pads[r] : nullptr;
     for (int r = 0; r < world; ++r) SOM_REQUIRE(pads->p[r] != nullptr, SOM_E_BADARG, "peer: null signal pad of rank %d", r);
     return SOM_OK;
+}
+// flag area of a rank (som_peer_signal_bytes): words [16 c, 16 c + 16) = the rank-to-rank flags of channel c,
+// words [64, 68) = the local block-arrival counters of the four channels
+static uint32_t* counter_of(const Pads& pads, int rank, int channel) { return pads.p[rank] + 64 + channel; }
+static int launch_barrier(const Pads& pads, int channel, int rank, int world, cudaStream_t st) {
+    barrier_kernel<<<1, 32, 0, st>>>(pads, channel, rank, world);
+    return check_launch("peer_barrier_kernel");
 }
 static int grid_for(int64_t n4) {
     int64_t g = ceil_div64(n4, (int64_t)THREADS * 4);
@@ -214,15 +249,16 @@ static int grid_for(int64_t n4) {
 using namespace som;
 using namespace som::peer;
 
-extern "C" size_t som_peer_signal_bytes(void) { return (size_t)4 * MAX_BLOCKS * MAX_WORLD * sizeof(uint32_t); }
+extern "C" size_t som_peer_signal_bytes(void) { return 1024; }
 
-extern "C" int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer_bufs, float* local_buf, int rank,
+extern "C" int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer_bufs, float* tail_out_f, int rank,
                                       int world, void* const* signal_pads, int channel, void* stream) {
+    float4* tail_out = (float4*)tail_out_f;
     SOM_REQUIRE(mc_buf != nullptr && n >= 0 && n % 4 == 0 && ((uintptr_t)mc_buf & 15) == 0, SOM_E_BADARG,
                 "peer_allreduce: n=%lld must be a multiple of 4 floats, 16-byte aligned", (long long)n);
     SOM_REQUIRE(channel >= 0 && channel < 4, SOM_E_BADARG, "peer: channel=%d", channel);
-    SOM_REQUIRE((peer_bufs == nullptr) == (local_buf == nullptr), SOM_E_BADARG,
-                "peer_allreduce: peer_bufs and local_buf go together");
+    SOM_REQUIRE((peer_bufs == nullptr) == (tail_out_f == nullptr) && ((uintptr_t)tail_out_f & 15) == 0, SOM_E_BADARG,
+                "peer_allreduce: peer_bufs and tail_out go together (tail_out 16-byte aligned)");
     Pads pads, bufs = {};
     int rc = make_pads(&pads, signal_pads, rank, world);
     if (rc) return rc;
@@ -235,10 +271,10 @@ extern "C" int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer
     }
     const int64_t per = ceil_div64(n4, world);
     const int64_t q0 = per * rank < n4 ? per * rank : n4, q1 = q0 + per < n4 ? q0 + per : n4;
-    // the grid must be the same on every rank (blocks pair up across ranks): size it for the largest slice
+    rc = launch_barrier(pads, channel, rank, world, (cudaStream_t)stream);
+    if (rc) return rc;
     allreduce_kernel<<<grid_for(per), THREADS, 0, (cudaStream_t)stream>>>(
-        (float*)mc_buf, q0, q1, q_tail, q_tail >= 0 ? (float4*)(local_buf + 4 * q_tail) : nullptr, bufs, pads, channel,
-        rank, world);
+        (float*)mc_buf, q0, q1, q_tail, tail_out, bufs, pads, counter_of(pads, rank, channel), channel, rank, world);
     return check_launch("peer_allreduce_kernel");
 }
 
@@ -258,10 +294,12 @@ extern "C" int som_peer_reduce_rows_f32(const void* mc_packed, void* const* peer
     rc = make_pads(&bufs, peer_packed, rank, world);
     if (rc) return rc;
     const int64_t d4 = D / 4;
-    // same grid on every rank: sized from max_rows, the largest row count any rank reduces
-    reduce_rows_kernel<<<grid_for((int64_t)max_rows * d4), THREADS, 0, (cudaStream_t)stream>>>(
+    rc = launch_barrier(pads, channel, rank, world, (cudaStream_t)stream);
+    if (rc) return rc;
+    (void)max_rows;
+    reduce_rows_kernel<<<grid_for((int64_t)(row1 - row0) * d4), THREADS, 0, (cudaStream_t)stream>>>(
         (const float*)mc_packed, (int64_t)row0 * d4, (int64_t)row1 * d4, (int64_t)K * d4, (float4*)out_rows,
-        (float4*)out_tail, bufs, pads, channel, rank, world);
+        (float4*)out_tail, bufs, world);
     return check_launch("peer_reduce_rows_kernel");
 }
 
@@ -275,8 +313,10 @@ extern "C" int som_peer_bcast_rows_f32(const float* src_rows, void* mc_dst_rows,
     Pads pads;
     int rc = make_pads(&pads, signal_pads, rank, world);
     if (rc) return rc;
-    bcast_rows_kernel<<<grid_for(max_n / 4), THREADS, 0, (cudaStream_t)stream>>>((const float4*)src_rows, (float*)mc_dst_rows,
-                                                                               n / 4, pads, channel, rank, world);
+    (void)max_n;
+    bcast_rows_kernel<<<grid_for(n / 4), THREADS, 0, (cudaStream_t)stream>>>((const float4*)src_rows, (float*)mc_dst_rows,
+                                                                           n / 4, pads, counter_of(pads, rank, channel),
+                                                                           channel, rank, world);
     return check_launch("peer_bcast_rows_kernel");
 }
 
@@ -293,8 +333,9 @@ extern "C" int som_peer_adam_slice_f32(const float* W_rows, void* mc_W_rows, flo
     Pads pads;
     int rc = make_pads(&pads, signal_pads, rank, world);
     if (rc) return rc;
-    adam_slice_bcast_kernel<<<grid_for(max_n / 4), THREADS, 0, (cudaStream_t)stream>>>(
+    (void)max_n;
+    adam_slice_bcast_kernel<<<grid_for(n / 4), THREADS, 0, (cudaStream_t)stream>>>(
         (const float4*)W_rows, (float*)mc_W_rows, (float4*)m_rows, (float4*)v_rows, (const float4*)g_rows, n / 4, D, lr, b1,
-        b2, (float)eps, steps_done, tail, loss_out, pads, channel, rank, world);
+        b2, (float)eps, steps_done, tail, loss_out, pads, counter_of(pads, rank, channel), channel, rank, world);
     return check_launch("peer_adam_slice_bcast_kernel");
 }

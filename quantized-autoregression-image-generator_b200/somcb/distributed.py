@@ -88,16 +88,20 @@ class DataParallelSom(SomTrainer):
       [lo_r, hi_r): it pulls the in-switch-reduced accumulator rows of its slice plus the filter's halo
       (``som_peer_reduce_rows_f32``: the reduce-scatter half, with overlap), filters them, runs Adam on its rows and
       stores the new rows into every rank's codebook (``som_peer_adam_slice_f32``: the all-gather fused into the
-      update); ``W~ = T @ W`` is computed per slice and broadcast the same way.  The non-shrinking part of a
-      strong-scaled step (two whole-codebook filters, Adam, a 4 MB all-reduce) becomes 1/R of the filters plus
-      three small kernels.  Falls back to one in-switch all-reduce (``som_peer_allreduce_f32``) + replicated tail when
+      update); ``W~ = T @ W`` is computed by every rank for the whole codebook (``wt="full"``, default) or per slice
+      and multicast the same way (``wt="slice"``).  Of the non-shrinking part of a strong-scaled step (two
+      whole-codebook filters, Adam, a 4 MB all-reduce) the gradient filter, Adam and the reduction become 1/R-sized.  Falls back to one in-switch all-reduce (``som_peer_allreduce_f32``) + replicated tail when
       the halo makes slicing pointless (slice + halo >= 3/4 of the units);
     * ``"auto"`` (default): ``"peer"`` when symmetric memory with multicast is available, else ``"nccl"``.
 
     Replicas stay bit-identical in every mode: a row is computed once, by its owner, and multicast."""
 
-    def __init__(self, codebook, lr, neighbourhood_step, group=None, tail="auto", **kw):
+    def __init__(self, codebook, lr, neighbourhood_step, group=None, tail="auto", wt="full", **kw):
         self.group = group
+        # peer tail: "full" (default) lets every rank compute W~ = T @ W for the whole codebook itself; "slice" computes
+        # it per slice and multicasts the rows, which costs one more cross-rank barrier per step (measured at 8 ranks:
+        # 0.781 ms per step against 0.749 ms with "full" -- the slice filter saves 17 us, the barrier costs more)
+        self.wt_mode = wt
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         super().__init__(codebook, lr, neighbourhood_step, world_size=world,
                          reduce_fn=self._allreduce if world > 1 else None, **kw)
@@ -163,7 +167,7 @@ class DataParallelSom(SomTrainer):
         lo, hi, g0, g1, max_own, max_halo = self._slices(ops.filter_half_width(k, rng))
         sig, rank, world = pm.signal_ptrs, pm.rank, pm.world
         sliced = 4 * max_halo <= 3 * k
-        if sliced:
+        if sliced and self.wt_mode == "slice":
             # W~ rows of the own slice from W[g0:g1] (complete on every rank: the previous step ended with the barrier
             # of the weight broadcast), multicast into every rank's W~
             if hi > lo:
@@ -193,9 +197,9 @@ class DataParallelSom(SomTrainer):
                                        sig, 2, betas=self.betas, eps=self.eps)
         else:
             ops.peer_allreduce(self._mc["packed"], kd + 4, rank, world, sig, 1, w.device,
-                               peer_ptrs=self._peer_packed, local=self.packed)
+                               peer_ptrs=self._peer_packed, tail_out=self._tail_local)
             grad = ops.neighbourhood_filter(self.packed[:kd].view(k, d), rng, scale=1.0)
-            loss = ops.adam_step_dp(w, self.m, self.v, grad, d, self.lr, self.t_dev, self.packed[kd:],
+            loss = ops.adam_step_dp(w, self.m, self.v, grad, d, self.lr, self.t_dev, self._tail_local,
                                     betas=self.betas, eps=self.eps)
         cb._norm_cache = None
         self.last_bmu = bmu

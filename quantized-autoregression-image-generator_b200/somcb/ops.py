@@ -365,15 +365,15 @@ def _pads(signal_ptrs):
     return (ctypes.c_void_p * len(signal_ptrs))(*[int(p) for p in signal_ptrs])
 
 
-def peer_allreduce(mc_ptr, n, rank, world, signal_ptrs, channel, device, peer_ptrs=None, local=None):
+def peer_allreduce(mc_ptr, n, rank, world, signal_ptrs, channel, device, peer_ptrs=None, tail_out=None):
     """In-place all-reduce(sum) of ``n`` floats at the multicast address ``mc_ptr`` (every rank calls it).  With
-    ``peer_ptrs`` / ``local`` (the buffer's peer addresses and this rank's tensor) the buffer is a packed accumulator
-    buffer whose 4-float tail is summed exactly."""
+    ``peer_ptrs`` / ``tail_out`` (the buffer's peer addresses and a separate local 4-float tensor) the buffer is a packed
+    accumulator buffer whose 4-float tail is summed exactly into ``tail_out``."""
     lib = _lib.load()
     with torch.cuda.device(device):
         check("som_peer_allreduce_f32",
               lib.som_peer_allreduce_f32(int(mc_ptr), int(n), _pads(peer_ptrs) if peer_ptrs is not None else None,
-                                         _ptr(local), int(rank), int(world), _pads(signal_ptrs), int(channel),
+                                         _ptr(tail_out), int(rank), int(world), _pads(signal_ptrs), int(channel),
                                          torch.cuda.current_stream(device).cuda_stream))
 
 
