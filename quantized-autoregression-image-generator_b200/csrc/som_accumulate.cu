@@ -133,7 +133,7 @@ __device__ __forceinline__ void store_vec(float* p, const float (&r)[VEC]) {
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(ACC_WARPS * 32, VEC == 4 ? 3 : 4)
+__global__ void __launch_bounds__(ACC_WARPS * 32, VEC == 4 ? 2 : 3)
 seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ skey,
                   const int* __restrict__ sid, const int* __restrict__ offsets,
                   const float* __restrict__ Wt, float* __restrict__ Rbar,
@@ -152,17 +152,22 @@ seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ s
     const int64_t p0 = c * S;
     const int64_t p1 = (p0 + S < n) ? p0 + S : n;
 
-    float acc[VEC], wt[VEC];
+    float acc[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; wt[i] = 0.f; }
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
     float sse = 0.f;
     int cur = -1;
     int64_t run_start = p0;
+    // keys just outside the chunk decide, without touching the offsets array, whether a segment lies inside the chunk
+    // (-> stored directly) or crosses an edge (-> partial slot): the same rule seg_level2_kernel applies to the offsets
+    const int prev_key = (p0 > 0) ? skey[p0 - 1] : -1;
+    const int next_key = (p1 < n) ? skey[p1] : -2;
 
-    auto flush = [&](int64_t /*run_end*/) {
+    auto flush = [&](int64_t run_end) {
         if (cur < 0 || !act) return;
-        int seg_lo = offsets[cur], seg_hi = offsets[cur + 1];
-        if (seg_lo >= p0 && seg_hi <= p1) {
+        const bool starts_inside = run_start > p0 || prev_key != cur;
+        const bool ends_inside = run_end < p1 || next_key != cur;
+        if (starts_inside && ends_inside) {
             store_vec<VEC>(Rbar + (int64_t)cur * D + d, acc);
         } else {
             int slot = (run_start == p0) ? 0 : 1;
@@ -170,26 +175,35 @@ seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ s
         }
     };
 
-    for (int64_t p = p0; p < p1; p += 8) {
-        // lanes 0..7 fetch (key, id) and compute the patch base for the 8 positions of this group
-        int my_key = -1;
-        int64_t my_base = 0;
+    // (key, patch base) of a group of 8 sorted positions: fetched by lanes 0..7 one group AHEAD of the rows they address
+    auto fetch = [&](int64_t p, int& k, int64_t& b) {
+        k = -1;
+        b = 0;
         if (lane < 8 && p + lane < p1) {
-            my_key = skey[p + lane];
-            my_base = patch_base(g, (int64_t)sid[p + lane]);
+            k = skey[p + lane];
+            b = patch_base(g, (int64_t)sid[p + lane]);
         }
-        float row[8][VEC];
+    };
+    int my_key;
+    int64_t my_base;
+    fetch(p0, my_key, my_base);
+    for (int64_t p = p0; p < p1; p += 8) {
+        float row[8][VEC], wtr[8][VEC];
         int key[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             key[u] = __shfl_sync(0xffffffffu, my_key, u);
             int64_t base = __shfl_sync(0xffffffffu, my_base, u);
-            if (key[u] >= 0 && act) load_vec<VEC>(row[u], x + base + doff);
-            else {
+            if (key[u] >= 0 && act) {
+                load_vec<VEC>(row[u], x + base + doff);
+                // the unit's W~ row travels with the patch row (L2-resident): no dependent load at a segment change
+                if (Wt != nullptr) load_vec<VEC>(wtr[u], Wt + (int64_t)key[u] * D + d);
+            } else {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) row[u][i] = 0.f;
+                for (int i = 0; i < VEC; ++i) { row[u][i] = 0.f; wtr[u][i] = 0.f; }
             }
         }
+        fetch(p + 8, my_key, my_base);                // next group's keys in flight while this one is consumed
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (key[u] < 0) break;                    // warp-uniform: past the chunk end
@@ -199,12 +213,11 @@ seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ s
                 run_start = p + u;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-                if (Wt != nullptr && act) load_vec<VEC>(wt, Wt + (int64_t)cur * D + d);
             }
             if (Wt != nullptr) {
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    float r = wt[i] - row[u][i];
+                    float r = wtr[u][i] - row[u][i];
                     acc[i] += r;
                     sse = fmaf(r, r, sse);
                 }
