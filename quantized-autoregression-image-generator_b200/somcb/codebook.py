@@ -68,8 +68,7 @@ class Codebook(nn.Module):
         self.num_embeddings = num_embeddings
         self.codebook = nn.Embedding(self.num_embeddings, self.embedding_dim)
         self.codebook.weight.data.uniform_(-1 / self.num_embeddings, 1 / self.num_embeddings)
-        # per-weights-version cache of ||c||^2; plain attribute, never in state_dict
-        self._norm_cache = None
+        self._norm_cache = None       # unused (kept so that code which reset the former ||c||^2 cache keeps working)
         self.bmu_variant = ops.SOM_BMU_AUTO
 
     # ---- reference API --------------------------------------------------------------------
@@ -140,11 +139,10 @@ class Codebook(nn.Module):
         return self.codebook.weight
 
     def _norms(self):
-        w = self.codebook.weight
-        key = (w._version, w.data_ptr(), w.device)
-        if self._norm_cache is None or self._norm_cache[0] != key:
-            self._norm_cache = (key, ops.prepare_codebook(w.detach()))
-        return self._norm_cache[1]
+        # ||c||^2 is recomputed on every call (one 2-3 us kernel): a cache keyed on the parameter's version counter
+        # goes stale silently whenever the weights are written through ``weight.data``, raw pointers, a collective
+        # or this library's own Adam kernels, and stale norms mean wrong BMUs
+        return ops.prepare_codebook(self.codebook.weight.detach())
 
     def _input(self, x, require_cuda=True):
         if x.dim() != 4:

@@ -131,7 +131,6 @@ class DataParallelSom(SomTrainer):
         with torch.no_grad():
             w_sym.copy_(cb.codebook.weight.data.reshape(-1))
             cb.codebook.weight.data = w_sym.view(k, d)       # the parameter now lives in peer-mapped memory
-        cb._norm_cache = None
         self.packed = packed
         self.peer = pm
         self._mc = {"packed": mc_packed, "w": mc_w, "wt": mc_wt}
@@ -201,14 +200,12 @@ class DataParallelSom(SomTrainer):
             grad = ops.neighbourhood_filter(self.packed[:kd].view(k, d), rng, scale=1.0)
             loss = ops.adam_step_dp(w, self.m, self.v, grad, d, self.lr, self.t_dev, self._tail_local,
                                     betas=self.betas, eps=self.eps)
-        cb._norm_cache = None
         self.last_bmu = bmu
         return loss
 
     def broadcast_weights(self, src=0):
         """Make every replica start from rank ``src``'s codebook."""
         dist.broadcast(self.cb.codebook.weight.data, src=src, group=self.group)
-        self.cb._norm_cache = None
 
 
 @torch.no_grad()

@@ -103,7 +103,6 @@ class SomTrainer:
             x_static.copy_(feature_map)
         graph.replay()
         self.t += 1
-        cb._norm_cache = None
         self.last_bmu = None
         self._bookkeeping()
         # the graph's own loss buffer (overwritten by the next replay of THIS graph): no copy kernel per step
@@ -140,7 +139,6 @@ class SomTrainer:
             # any of the step's kernels at this size
             loss, self.last_bmu = ops.step_small(x, geom, w, self.m, self.v, rng, self.lr, self.t_dev,
                                                  betas=self.betas, eps=self.eps)
-            cb._norm_cache = None
             return loss
 
         wt = ops.neighbourhood_filter(w, rng)
@@ -155,7 +153,6 @@ class SomTrainer:
         grad = ops.neighbourhood_filter(packed[:kd].view(k, d), rng, scale=1.0)
         loss = ops.adam_step_dp(w, self.m, self.v, grad, d, self.lr, self.t_dev, packed[kd:], betas=self.betas,
                                 eps=self.eps)
-        cb._norm_cache = None                          # W changed under torch's feet
         self.last_bmu = bmu
         return loss
 
