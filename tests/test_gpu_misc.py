@@ -125,13 +125,17 @@ def test_host_tokenizer_matches_direct_call():
     cb = cb.to(DEV)
     host = synthetic_fmaps(1000, 5).pin_memory()
     tok = somcb.HostTokenizer(cb, chunk_fmaps=192, depth=3)     # ragged last chunk, slot reuse
-    got = tok.tokenize(host)
-    torch.cuda.synchronize()
     want = cb.get_patches_bmu(host.to(DEV), reshape=True).cpu()
+    torch.cuda.synchronize()
+    got = tok.tokenize(host)                     # synchronous by default: valid on return, no device sync here
     assert got.shape == (1000, 256) and torch.equal(got, want)
     got2 = tok.tokenize(host)
-    torch.cuda.synchronize()
     assert torch.equal(got2, want)
+    out = torch.empty(1000, 256, dtype=torch.int64, pin_memory=True)
+    got3 = tok.tokenize(host, out, sync=False)   # asynchronous form: wait on the tokenizer's event
+    assert tok.done is not None
+    tok.done.synchronize()
+    assert got3 is out and torch.equal(out, want)
 
 
 def test_reference_tokenisation_call_sequence():
@@ -201,10 +205,45 @@ def test_shard_reader_feeds_host_tokenizer(tmp_path):
     counts = None
     for lo, hi, batch in reader.batches():
         idx = tok.tokenize(batch)
-        torch.cuda.synchronize()
         assert torch.equal(idx, ref[lo:hi])
         counts = ops.histogram(idx.to(DEV).reshape(-1), k, counts)
     assert torch.equal(counts.cpu(), torch.bincount(ref.reshape(-1), minlength=k))
+    # asynchronous consumer: the reader must not refill a pinned staging buffer that a copy is still reading
+    outs, evs = [], []
+    for lo, hi, batch in reader.batches():
+        dst = torch.empty(batch.shape, device=DEV)
+        dst.copy_(batch, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        reader.mark_in_flight(ev)
+        outs.append((lo, hi, dst))
+    torch.cuda.synchronize()
+    for lo, hi, dst in outs:
+        assert torch.equal(dst.cpu(), x[lo:hi])
+
+
+def test_host_trainer_matches_device_trainer():
+    """somcb.HostTrainer (pinned host batches, H2D on a copy stream, step graph on the staging buffers, loss through a
+    pinned scalar) == the same steps on device-resident batches, bit for bit."""
+    pd, k = (4, 4), 2048
+    w0 = trained_like_codebook(k, pd, 7)
+    trainers = []
+    for _ in range(2):
+        cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                            init_neighbour_range=k // 2)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(w0)
+        trainers.append(somcb.SomTrainer(cb.to(DEV), lr=1e-4, neighbourhood_step=4, use_cuda_graph="alias"))
+    ht = somcb.HostTrainer(trainers[0], depth=2)
+    hosts = [synthetic_fmaps(96, 40 + i).pin_memory() for i in range(7)]
+    pend = [ht.step(h) for h in hosts[:2]]
+    losses = [p.item() for p in pend]
+    for h in hosts[2:]:
+        losses.append(ht.step(h).item())
+    want = [float(trainers[1].step(h.to(DEV))) for h in hosts]
+    assert losses == want
+    assert torch.equal(trainers[0].cb.codebook.weight.data, trainers[1].cb.codebook.weight.data)
+    assert trainers[0].cb.neighbourhood_range == trainers[1].cb.neighbourhood_range == k // 2 - 1
 
 
 def test_tokenize_pair_matches_reference_golden():
