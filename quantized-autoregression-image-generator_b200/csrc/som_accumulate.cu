@@ -24,8 +24,13 @@
 #include <cub/device/device_radix_sort.cuh>
 
 namespace som {
+SOM_TRACE_TU(trace_set_accumulate)
 
 constexpr int ACC_WARPS = 8;
+
+constexpr int CS_BLOCK = 2048;      // patches per block of the counting sort
+constexpr int CS_THREADS = 1024;
+constexpr int CS_KMAX = 16384;      // bins that fit in shared memory (64 KB)
 
 struct AccumPlan {
     int64_t n;
@@ -35,7 +40,9 @@ struct AccumPlan {
     int n_slices_max;      // slices at VEC=1 (upper bound used for sizing)
     int end_bit;
     size_t off_keys_a, off_keys_b, off_vals_a, off_vals_b, off_offsets, off_partial, off_sse,
-        off_cub, cub_bytes, total;
+        off_cub, cub_bytes, off_hist, total;
+    int cs_blocks;         // > 0: our own counting sort (K <= 16 384), else cub's radix sort
+    int cs_per;            // patches per block of it: CS_BLOCK, or more once that would be over one block per SM
 };
 
 // Sorted positions per level-1 chunk: enough (chunk, feature slice) warps to fill the machine, but no shorter chunks
@@ -83,12 +90,18 @@ static int make_plan(AccumPlan* pl, int64_t n, int D, int K, bool query_cub) {
         pl->cub_bytes = bytes;
     }
     pl->off_cub = take(pl->cub_bytes + 256);
+    // counting sort: per-block histograms (ints) + the totals; blocks x K x 4 bytes (4 MB at 131 072 patches, 32 MB at 2^20)
+    pl->cs_per = CS_BLOCK;
+    if (n > (int64_t)148 * CS_BLOCK) pl->cs_per = (int)(ceil_div64(ceil_div64(n, 148), CS_THREADS) * CS_THREADS);
+    pl->cs_blocks = (K <= CS_KMAX && n > 0 && n <= ((int64_t)1 << 22)) ? (int)ceil_div64(n, pl->cs_per) : 0;
+    pl->off_hist = take(pl->cs_blocks > 0 ? ((size_t)pl->cs_blocks + 1) * K * 4 : 0);
     pl->total = o;
     return SOM_OK;
 }
 
 __global__ void __launch_bounds__(256) pairs_kernel(const int64_t* __restrict__ bmu, int64_t n, int K,
                                                     int* __restrict__ keys, int* __restrict__ vals) {
+    trace_stamp(s_trace_buf, 8);
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
     int64_t k = bmu[p];
@@ -101,11 +114,175 @@ __global__ void __launch_bounds__(256) pairs_kernel(const int64_t* __restrict__ 
 // (possibly empty) range of unit ids between its left and right neighbour keys.
 __global__ void __launch_bounds__(256) offsets_kernel(const int* __restrict__ skey, int64_t n, int K,
                                                       int* __restrict__ offsets) {
+    trace_stamp(s_trace_buf, 9);
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p > n) return;
     int lo = (p == 0) ? -1 : skey[p - 1];
     int hi = (p == n) ? K : skey[p];
     for (int a = lo + 1; a <= hi; ++a) offsets[a] = (int)p;
+}
+
+// ---- stable counting sort of (unit, patch) by unit, for codebooks of up to 16 384 units --------------------------------------
+// Replaces pairs_kernel + the four launches of cub::DeviceRadixSort (two 7-bit passes) + offsets_kernel by four short
+// kernels of our own: a one-pass sort on the whole key is possible because K bins fit in shared memory (64 KB).
+//   csort_hist      block b (CS_BLOCK patches): histogram of its keys in shared memory -> hist[b][K]
+//   csort_prefix    thread per key: exclusive prefix over the blocks in place, total[k]
+//   csort_offsets   one CTA: exclusive scan of the totals -> offsets[0..K] (what offsets_kernel derived from the sorted keys)
+//   csort_scatter   block b: every patch goes to offsets[key] + hist[b][key] + its rank among the block's earlier
+//                   patches of the same key (warps take turns, match groups inside a warp): STABLE, so the patches of a
+//                   unit stay in ascending order and the segmented sums keep their fixed order
+
+__global__ void __launch_bounds__(CS_THREADS) csort_hist_kernel(const int64_t* __restrict__ bmu, int64_t n, int K, int per,
+                                                                int* __restrict__ hist) {
+    trace_stamp(s_trace_buf, 8);
+    extern __shared__ int cs_bins[];
+    for (int k = threadIdx.x; k < K; k += CS_THREADS) cs_bins[k] = 0;
+    __syncthreads();
+    const int64_t p0 = (int64_t)blockIdx.x * per;
+#pragma unroll 2
+    for (int u = 0; u < per; u += CS_THREADS) {
+        const int64_t p = p0 + u + threadIdx.x;
+        if (p < n) {
+            int64_t k = bmu[p];
+            k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+            atomicAdd(&cs_bins[(int)k], 1);
+        }
+    }
+    __syncthreads();
+    int* out = hist + (int64_t)blockIdx.x * K;
+    for (int k = threadIdx.x; k < K; k += CS_THREADS) out[k] = cs_bins[k];
+}
+
+__global__ void __launch_bounds__(256) csort_prefix_kernel(int* __restrict__ hist, int nb, int K, int* __restrict__ total) {
+    trace_stamp(s_trace_buf, 20);
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= K) return;
+    constexpr int G = 32;                                  // loads in flight per thread: the loop is a chain of L2 round trips
+    int run = 0;
+    for (int b0 = 0; b0 < nb; b0 += G) {
+        int v[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) v[u] = (b0 + u < nb) ? hist[(int64_t)(b0 + u) * K + k] : 0;
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            if (b0 + u < nb) { hist[(int64_t)(b0 + u) * K + k] = run; run += v[u]; }
+        }
+    }
+    total[k] = run;
+}
+
+// offsets[a] = number of patches with key < a, a in [0, K]: one CTA; thread t holds keys t, 1024 + t, ... (coalesced:
+// one SM pays a wavefront per touched sector, a thread-owns-16-consecutive-keys layout cost 15 us here), all loaded up
+// front; warp scans of the 16 rows run side by side, then one scan over the 512 (row, warp) sums in key order
+__global__ void __launch_bounds__(1024) csort_offsets_kernel(const int* __restrict__ total, int K, int* __restrict__ offsets) {
+    trace_stamp(s_trace_buf, 21);
+    constexpr int PER = CS_KMAX / 1024;
+    __shared__ int row_warp_s[PER * 32];
+    __shared__ int group_s[PER];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int v[PER], inc[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int k = u * 1024 + (int)threadIdx.x;
+        v[u] = k < K ? total[k] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) inc[u] = v[u];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int t = __shfl_up_sync(0xffffffffu, inc[u], o);
+            if (lane >= o) inc[u] += t;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) row_warp_s[u * 32 + warp] = inc[u];
+    }
+    __syncthreads();
+    int mine = 0, mine_inc = 0;
+    if (threadIdx.x < PER * 32) {                            // warps 0..15: inclusive scan of 32 sums each
+        mine = row_warp_s[threadIdx.x];
+        mine_inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, mine_inc, o);
+            if (lane >= o) mine_inc += t;
+        }
+        if (lane == 31) group_s[warp] = mine_inc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int g = lane < PER ? group_s[lane] : 0;
+        int gi = g;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, gi, o);
+            if (lane >= o) gi += t;
+        }
+        if (lane < PER) group_s[lane] = gi - g;              // exclusive over the rows
+        if (lane == PER - 1) offsets[K] = gi;
+    }
+    __syncthreads();
+    if (threadIdx.x < PER * 32) row_warp_s[threadIdx.x] = group_s[warp] + mine_inc - mine;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int k = u * 1024 + (int)threadIdx.x;
+        if (k < K) offsets[k] = row_warp_s[u * 32 + warp] + inc[u] - v[u];
+    }
+    trace_stamp(s_trace_buf, 121);
+}
+
+__global__ void __launch_bounds__(CS_THREADS) csort_scatter_kernel(const int64_t* __restrict__ bmu, int64_t n, int K, int per,
+                                                                   const int* __restrict__ hist,
+                                                                   const int* __restrict__ offsets,
+                                                                   int* __restrict__ skey, int* __restrict__ sid) {
+    trace_stamp(s_trace_buf, 22);
+    extern __shared__ int cs_bins[];                        // patches of the block seen so far, per key
+    for (int k = threadIdx.x; k < K; k += CS_THREADS) cs_bins[k] = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int* blk = hist + (int64_t)blockIdx.x * K;
+    const int64_t p0 = (int64_t)blockIdx.x * per;
+    auto key_of = [&](int64_t p) -> int {
+        if (p >= n) return -1;
+        const int64_t k = bmu[p];
+        return (int)(k < 0 ? 0 : (k >= K ? K - 1 : k));
+    };
+    int key_next = key_of(p0 + threadIdx.x);
+    __syncthreads();
+#pragma unroll 1
+    for (int u = 0; u < per; u += CS_THREADS) {
+        const int64_t p = p0 + u + threadIdx.x;
+        const int key = key_next;
+        if (u + CS_THREADS < per) key_next = key_of(p + CS_THREADS);       // next round's keys fly during the turns
+        // where the block's patches of this key start: two gathers, needed only AFTER the turns (kept out of them --
+        // a first version let the compiler sink them into the turn and paid an L2 round trip per warp turn)
+        int base = 0;
+        if (key >= 0) base = offsets[key] + blk[key];
+        // lanes of the warp with the same key: rank inside the group, the group's last lane updates the bin
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const int rank_in_warp = __popc(grp & ((1u << lane) - 1u));
+        const int add = ((grp >> lane) == 1u) ? __popc(grp) : 0;
+        int local = 0;
+#pragma unroll 1
+        for (int w = 0; w < CS_THREADS / 32; ++w) {          // warps take turns: ascending patch order per key
+            if (warp == w) {                                 // (one full-warp sync: a sync per match group serialised them)
+                if (key >= 0) local = cs_bins[key];
+                __syncwarp();
+                if (add && key >= 0) cs_bins[key] = local + add;
+            }
+            __syncthreads();
+        }
+        if (key >= 0) {
+            const int pos = base + local + rank_in_warp;
+            skey[pos] = key;
+            sid[pos] = (int)p;
+        }
+    }
+    __syncthreads();
+    trace_stamp(s_trace_buf, 122);
 }
 
 template <int VEC> struct VecT;
@@ -139,6 +316,7 @@ seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ s
                   const float* __restrict__ Wt, float* __restrict__ Rbar,
                   float* __restrict__ partial, double* __restrict__ sse_part,
                   int S, int64_t n_chunks, int n_slices) {
+    trace_stamp(s_trace_buf, 10);
     const int lane = threadIdx.x & 31;
     const int64_t wg = blockIdx.x * (int64_t)ACC_WARPS + (threadIdx.x >> 5);
     const int64_t c = wg / n_slices;
@@ -239,6 +417,7 @@ __global__ void __launch_bounds__(ACC_WARPS * 32)
 seg_level2_kernel(const int* __restrict__ offsets, const float* __restrict__ partial,
                   float* __restrict__ Rbar, int64_t* __restrict__ counts, int K, int D, int S,
                   int n_slices) {
+    trace_stamp(s_trace_buf, 11);
     const int lane = threadIdx.x & 31;
     const int64_t wg = blockIdx.x * (int64_t)ACC_WARPS + (threadIdx.x >> 5);
     const int64_t a = wg / n_slices;
@@ -289,6 +468,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 acc_scan_kernel(const float* __restrict__ x, Geom g, const int64_t* __restrict__ bmu, int K,
                 const float* __restrict__ Wt, float* __restrict__ Rbar, int64_t* __restrict__ counts,
                 double* __restrict__ sse_part, int n_slices) {
+    trace_stamp(s_trace_buf, 10);
     __shared__ int list[SCAN_CH];
     __shared__ int n_list;
     __shared__ float sse_w[SCAN_THREADS / 32];
@@ -385,6 +565,7 @@ acc_scan_kernel(const float* __restrict__ x, Geom g, const int64_t* __restrict__
 __global__ void __launch_bounds__(1024) sse_reduce_kernel(const double* __restrict__ part, int64_t m,
                                                           double* __restrict__ out, float* __restrict__ tail,
                                                           int64_t n_patches) {
+    trace_stamp(s_trace_buf, 12);
     __shared__ double sh[1024];
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < m; i += 1024) s += part[i];
@@ -499,6 +680,31 @@ static int accumulate_impl(const float* x, int64_t n_img, int C, int H, int Wd, 
 
     const int* skey = keys_a;
     const int* sid = vals_a;
+    if (n > 0 && pl.cs_blocks > 0) {
+        int* hist = (int*)(base + pl.off_hist);
+        int* total = hist + (size_t)pl.cs_blocks * K;
+        const size_t bins = (size_t)K * sizeof(int);
+        static PerDeviceFlag attr_done;
+        if (attr_done.pending()) {
+            cudaError_t e = cudaFuncSetAttribute(csort_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_KMAX * 4);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(csort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_KMAX * 4);
+            if (e != cudaSuccess) { set_error("accumulate: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
+            attr_done.set();
+        }
+        csort_hist_kernel<<<pl.cs_blocks, CS_THREADS, bins, st>>>(bmu, n, K, pl.cs_per, hist);
+        rc = check_launch("csort_hist_kernel");
+        if (rc) return rc;
+        csort_prefix_kernel<<<(unsigned)ceil_div64(K, 256), 256, 0, st>>>(hist, pl.cs_blocks, K, total);
+        rc = check_launch("csort_prefix_kernel");
+        if (rc) return rc;
+        csort_offsets_kernel<<<1, 1024, 0, st>>>(total, K, offsets);
+        rc = check_launch("csort_offsets_kernel");
+        if (rc) return rc;
+        csort_scatter_kernel<<<pl.cs_blocks, CS_THREADS, bins, st>>>(bmu, n, K, pl.cs_per, hist, offsets, keys_a, vals_a);
+        rc = check_launch("csort_scatter_kernel");
+        if (rc) return rc;
+    } else {
     if (n > 0) {
         pairs_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(bmu, n, K, keys_a, vals_a);
         rc = check_launch("pairs_kernel");
@@ -513,6 +719,7 @@ static int accumulate_impl(const float* x, int64_t n_img, int C, int H, int Wd, 
     offsets_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, st>>>(skey, n, K, offsets);
     rc = check_launch("offsets_kernel");
     if (rc) return rc;
+    }
 
     int vec = g.vec;
     if (Wt != nullptr && ((uintptr_t)Wt & 15) != 0) vec = 1;

@@ -36,6 +36,7 @@
 #include <cuda_fp16.h>
 
 namespace som {
+SOM_TRACE_TU(trace_set_l16)
 namespace tcl16 {
 using namespace tc;
 
@@ -107,6 +108,7 @@ __device__ long long g_prof16[8];             // CTA 0's MMA loop: cycles, tiles
 template <int CG, bool MERGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
+    trace_stamp(s_trace_buf, 7);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int B_STAGE = B_BLK_BYTES / CG;       // this CTA's share of a 256-unit block
@@ -526,6 +528,7 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 // An all-zero or non-finite codebook keeps both at 1.  One CTA over the K norms.
 __device__ __forceinline__ void scales_from_max_norm(float mn, float* out2);
 __global__ void __launch_bounds__(1024) cb_scale_l_kernel(const float* __restrict__ cn, int K, float* __restrict__ scale_out) {
+    trace_stamp(s_trace_buf, 6);
     __shared__ float sh[32];
     float mn = 0.f;
     for (int i = threadIdx.x; i < K; i += 1024) mn = fmaxf(mn, fabsf(__ldg(cn + i)));
@@ -566,6 +569,7 @@ __global__ void __launch_bounds__(256) split_w_l16_kernel(const float* __restric
                                                           int K, int D, int DB, int K_pad,
                                                           float* __restrict__ scale, __half* __restrict__ Bp,
                                                           __half* __restrict__ Tp) {
+    trace_stamp(s_trace_buf, 6);
     __shared__ float sh_max[8];
     __shared__ float sh_scale[2];
     if (OWN_SCALE) {

@@ -70,6 +70,22 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---- device-timestamp tracer (debug only: off unless som_debug_trace() handed the library a buffer) -------------------
+// The first thread of an instrumented kernel appends (kernel id, %globaltimer) when the kernel starts; the differences
+// between consecutive entries are the kernels' durations including the gaps between them -- what CUDA events cannot
+// show inside a replayed graph, and ncu cannot show for a multi-rank run.  buf[0] = number of entries.
+__device__ __forceinline__ void trace_stamp(unsigned long long* buf, int id) {
+    if (buf != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+        const unsigned long long slot = atomicAdd(buf, 1ull);
+        if (slot < 4000ull) { buf[1 + 2 * slot] = (unsigned long long)id; buf[2 + 2 * slot] = t; }
+    }
+}
+#define SOM_TRACE_TU(setter)                                                            \
+    static __device__ unsigned long long* s_trace_buf = nullptr;                        \
+    void setter(unsigned long long* p) { cudaMemcpyToSymbol(s_trace_buf, &p, sizeof(p)); }
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -7,6 +7,7 @@
 #include <string.h>
 
 namespace som {
+SOM_TRACE_TU(trace_set_core)
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
@@ -88,6 +89,7 @@ int make_geom(Geom* g, const void* x, int64_t n_img, int C, int H, int W, int pH
 template <int G, int U, int J>
 __global__ void __launch_bounds__(256) norm2_kernel(const float* __restrict__ W, int K, int D,
                                                     float* __restrict__ out) {
+    trace_stamp(s_trace_buf, 5);
     constexpr int RPW = (32 / G) * U;                       // units per warp per iteration
     const int lane = threadIdx.x & (G - 1);
     const int sub = (threadIdx.x & 31) / G;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(256) norm2_kernel(const float* __restrict__ W,
 // order (four loads in flight), then a warp butterfly and the eight warp sums in warp order: fixed order, and the
 // rule depends on D only, so a unit's norm does not depend on how many units the launch (or the shard) holds.
 __global__ void __launch_bounds__(256) norm2_long_kernel(const float* __restrict__ W, int D, float* __restrict__ out) {
+    trace_stamp(s_trace_buf, 5);
     __shared__ float part[8];
     const float* row = W + (int64_t)blockIdx.x * D;
     float s = 0.f;
@@ -472,6 +475,7 @@ __device__ __forceinline__ void adam_body(float* __restrict__ W, float* __restri
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ W, float* __restrict__ m,
                                                    float* __restrict__ v, const float* __restrict__ g,
                                                    int64_t n, AdamScalars a) {
+    trace_stamp(s_trace_buf, 19);
     adam_body(W, m, v, g, n, a);
 }
 
@@ -481,6 +485,7 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ W, fl
                                                        float* __restrict__ v, const float* __restrict__ g,
                                                        int64_t n, double lr, double b1, double b2, float eps,
                                                        const int64_t* __restrict__ steps_done) {
+    trace_stamp(s_trace_buf, 19);
     const double t = (double)(*steps_done + 1);
     AdamScalars a;
     a.w1 = (float)(1.0 - b1); a.b2 = (float)b2; a.one_m_b2 = (float)(1.0 - b2);
@@ -500,6 +505,7 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(float* __restrict__ W, flo
                                                       int64_t n, int D, double lr, double b1, double b2, float eps,
                                                       int64_t* __restrict__ steps_done,
                                                       const float* __restrict__ tail, double* __restrict__ loss_out) {
+    trace_stamp(s_trace_buf, 18);
     const double t = (double)(steps_done[0] + 1);
     const double numel = ((double)tail[2] * 4096.0 + (double)tail[3]) * (double)D;
     const float gscale = (float)(2.0 / numel);
@@ -592,6 +598,21 @@ static inline int grid_for(int64_t work_items, int threads, int per_sm) {
 }  // namespace som
 
 using namespace som;
+
+namespace som {
+void trace_set_filter_tc(unsigned long long*);
+void trace_set_filter(unsigned long long*);
+void trace_set_l16(unsigned long long*);
+void trace_set_accumulate(unsigned long long*);
+void trace_set_peer(unsigned long long*);
+}  // namespace som
+
+// debug: hand every translation unit the trace buffer (8 KB + 64 KB of device memory, zero-filled; NULL switches it off)
+extern "C" SOM_API int som_debug_trace(unsigned long long* buf) {
+    som::trace_set_core(buf); som::trace_set_filter_tc(buf); som::trace_set_filter(buf); som::trace_set_l16(buf);
+    som::trace_set_accumulate(buf); som::trace_set_peer(buf);
+    return (int)cudaGetLastError();
+}
 
 extern "C" {
 

@@ -15,6 +15,7 @@
 #include "som_common.cuh"
 
 namespace som {
+SOM_TRACE_TU(trace_set_filter)
 
 constexpr int FILT_TA = 8;          // units per warp
 constexpr int FILT_WARPS = 8;       // warps per CTA  -> 64 units x 32 features per CTA
@@ -24,6 +25,7 @@ constexpr int FILT_PAD = FILT_TA + 8;
 __global__ void __launch_bounds__(FILT_WARPS * 32)
 filter_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int D,
               float two_var, int h, float scale) {
+    trace_stamp(s_trace_buf, 4);
     extern __shared__ float tab[];
     const int off = h + FILT_PAD;
     const int tab_n = 2 * off + 1;
@@ -102,6 +104,7 @@ template <int TD, int JS>
 __global__ void __launch_bounds__(FT_THREADS)
 filter_tile_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int D,
                    float two_var, int h, float scale) {
+    trace_stamp(s_trace_buf, 4);
     constexpr int FG = TD / 4;                     // feature groups (threads) per row
     constexpr int UG = FT_THREADS / (FG * JS);     // unit groups per CTA
     constexpr int FT_TK = UG * FT_U;               // units per CTA (32)

@@ -26,6 +26,7 @@
 #include "som_tc_ptx.cuh"
 
 namespace som {
+SOM_TRACE_TU(trace_set_filter_tc)
 namespace ftc {
 using namespace tc;
 
@@ -73,6 +74,7 @@ __device__ __forceinline__ void mma_tf32_n(uint32_t tmem_d, uint64_t adesc, uint
 // memory: reads coalesced along d, writes coalesced along j.
 __global__ void __launch_bounds__(256) split_in_t_kernel(const float* __restrict__ in, int K, int D, int h, int Kp,
                                                          float* __restrict__ Bhi, float* __restrict__ Blo) {
+    trace_stamp(s_trace_buf, 1);
     __shared__ float tile[32][33];
     const int jp0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -98,6 +100,7 @@ template <int TNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                  const Params P) {
+    trace_stamp(s_trace_buf, 2);
     constexpr int STAGE = stage_bytes<TNF>();
     constexpr int B_BYTES = TNF * KBLK * 4;
     extern __shared__ uint8_t smem_raw[];
@@ -271,6 +274,7 @@ done:
 // out = scale * (((p0 + p1) + p2) + p3): the unsplit epilogue's order
 __global__ void __launch_bounds__(256) filter_reduce_kernel(const float* __restrict__ partial, int64_t n, float scale,
                                                             float* __restrict__ out) {
+    trace_stamp(s_trace_buf, 3);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         float v = partial[i];

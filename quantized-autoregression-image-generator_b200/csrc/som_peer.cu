@@ -26,6 +26,7 @@
 #include "som_common.cuh"
 
 namespace som {
+SOM_TRACE_TU(trace_set_peer)
 namespace peer {
 
 constexpr int MAX_WORLD = 16;
@@ -50,8 +51,9 @@ __device__ __forceinline__ uint32_t cas_sys(uint32_t* addr, uint32_t cmp, uint32
 // the rank-to-rank signal exchange on behalf of all blocks, so a kernel costs `world` remote atomics instead of
 // blocks x world (measured at 8 ranks: the per-block form spent most of the tail's time in NVLink atomics).
 // Call after the block's global / multicast stores; `counter` is a zero-initialised word of this rank's flag area.
+// Returns true in the block that ran the exchange (the last one to arrive).
 template <bool PREV, bool NEXT>
-__device__ __forceinline__ void grid_sync_ranks(const Pads& pads, uint32_t* counter, int channel, int rank, int world) {
+__device__ __forceinline__ bool grid_sync_ranks(const Pads& pads, uint32_t* counter, int channel, int rank, int world) {
     __shared__ int is_last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -72,10 +74,12 @@ __device__ __forceinline__ void grid_sync_ranks(const Pads& pads, uint32_t* coun
                 if (gtimer() > deadline) __trap();
         }
     }
+    return is_last != 0;
 }
 
 // one-block barrier over the ranks: everything this rank enqueued before it is visible to the peers' later kernels
 __global__ void __launch_bounds__(32) barrier_kernel(Pads pads, int channel, int rank, int world) {
+    trace_stamp(s_trace_buf, 13);
     if ((int)threadIdx.x < world) {
         __threadfence_system();
         const int peer = threadIdx.x;
@@ -87,6 +91,8 @@ __global__ void __launch_bounds__(32) barrier_kernel(Pads pads, int channel, int
         while (cas_sys<2>(get, 1u, 0u) != 1u)
             if (gtimer() > deadline) __trap();
     }
+    __syncwarp();
+    trace_stamp(s_trace_buf, 113);                               // every peer has arrived
 }
 
 __device__ __forceinline__ float4 mm_ld_reduce(const float* mc) {
@@ -126,6 +132,7 @@ __device__ __forceinline__ float4 exact_tail(const Pads& bufs, int64_t q_tail, i
 __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q0, int64_t q1, int64_t q_tail,
                                                             float4* __restrict__ tail_out, Pads bufs, Pads pads,
                                                             uint32_t* counter, int channel, int rank, int world) {
+    trace_stamp(s_trace_buf, 17);
     // (barrier_kernel ran before this launch: every rank's input is complete)
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q_tail >= 0 && blockIdx.x == 0 && threadIdx.x == 0) tail = exact_tail(bufs, q_tail, world);
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q
         for (int u = 0; u < 4; ++u)
             if (q + u * stride < q1) mm_st(mc + 4 * (q + u * stride), v[u]);
     }
-    __threadfence_system();
+    // (no fence per thread: grid_sync_ranks' bar.sync + thread 0's system fence is cumulative over the block's stores)
     grid_sync_ranks<true, true>(pads, counter, channel, rank, world);   // every slice has landed everywhere, every tail was read
     // (the exact tail goes to a SEPARATE local buffer: peers may still be reading this rank's in-place tail)
     if (q_tail >= 0 && blockIdx.x == 0 && threadIdx.x == 0) *tail_out = tail;
@@ -150,6 +157,7 @@ __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q
 __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(const float* mc, int64_t q0, int64_t q1, int64_t q_tail,
                                                               float4* __restrict__ out, float4* __restrict__ tail_out,
                                                               Pads bufs, int world) {
+    trace_stamp(s_trace_buf, 14);
     // (barrier_kernel ran before this launch: every rank's accumulators are complete)
     const int64_t stride = (int64_t)gridDim.x * THREADS;
     for (int64_t q = q0 + blockIdx.x * (int64_t)THREADS + threadIdx.x; q < q1; q += 4 * stride) {
@@ -167,9 +175,9 @@ __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(const float* mc, i
 // local rows -> the same rows of every rank (multicast store), then the cross-rank barrier that makes them visible
 __global__ void __launch_bounds__(THREADS) bcast_rows_kernel(const float4* __restrict__ src, float* mc_dst, int64_t n4,
                                                              Pads pads, uint32_t* counter, int channel, int rank, int world) {
+    trace_stamp(s_trace_buf, 16);
     const int64_t stride = (int64_t)gridDim.x * THREADS;
     for (int64_t q = blockIdx.x * (int64_t)THREADS + threadIdx.x; q < n4; q += stride) mm_st(mc_dst + 4 * q, src[q]);
-    __threadfence_system();
     grid_sync_ranks<true, true>(pads, counter, channel, rank, world);
 }
 
@@ -194,6 +202,7 @@ __global__ void __launch_bounds__(THREADS) adam_slice_bcast_kernel(const float4*
                                                                    const float* __restrict__ tail,
                                                                    double* __restrict__ loss_out, Pads pads,
                                                                    uint32_t* counter, int channel, int rank, int world) {
+    trace_stamp(s_trace_buf, 15);
     const double t = (double)(steps_done[0] + 1);
     const double numel = ((double)tail[2] * 4096.0 + (double)tail[3]) * (double)D;
     const float gs = (float)(2.0 / numel);
@@ -214,14 +223,9 @@ __global__ void __launch_bounds__(THREADS) adam_slice_bcast_kernel(const float4*
         m[q] = mq; v[q] = vq;
         mm_st(mc_W + 4 * q, wq);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {                  // last block to arrive advances the step count (steps_done[1]: arrival counter)
-        __threadfence();
-        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(steps_done + 1), 1ull);
-        if (old == (unsigned long long)gridDim.x - 1ull) { steps_done[1] = 0; steps_done[0] += 1; }
-    }
-    grid_sync_ranks<true, true>(pads, counter, channel, rank, world);
+    // the last block to arrive (every block has read steps_done[0] by then) runs the exchange and advances the step count
+    const bool last = grid_sync_ranks<true, true>(pads, counter, channel, rank, world);
+    if (last && threadIdx.x == 0) steps_done[0] += 1;
 }
 
 static int make_pads(Pads* pads, void* const* signal_pads, int rank, int world) {
@@ -238,9 +242,12 @@ static int launch_barrier(const Pads& pads, int channel, int rank, int world, cu
     barrier_kernel<<<1, 32, 0, st>>>(pads, channel, rank, world);
     return check_launch("peer_barrier_kernel");
 }
+// One quad per thread while that stays within two blocks per SM: these kernels are latency-bound (a multimem load or a
+// store + fence is a round trip through the switch), so the work is spread wide instead of looped (round 2 first
+// version: 4 quads per thread, <= 48 blocks -- the Adam slice of 2048 rows ran on 16 SMs, four serial round trips each).
 static int grid_for(int64_t n4) {
-    int64_t g = ceil_div64(n4, (int64_t)THREADS * 4);
-    return (int)(g < 1 ? 1 : (g > 48 ? 48 : g));
+    int64_t g = ceil_div64(n4, (int64_t)THREADS);
+    return (int)(g < 1 ? 1 : (g > 296 ? 296 : g));
 }
 
 }  // namespace peer
