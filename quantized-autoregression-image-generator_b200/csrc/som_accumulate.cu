@@ -101,6 +101,7 @@ static int make_plan(AccumPlan* pl, int64_t n, int D, int K, bool query_cub) {
 
 __global__ void __launch_bounds__(256) pairs_kernel(const int64_t* __restrict__ bmu, int64_t n, int K,
                                                     int* __restrict__ keys, int* __restrict__ vals) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 8);
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) pairs_kernel(const int64_t* __restrict__ 
 // (possibly empty) range of unit ids between its left and right neighbour keys.
 __global__ void __launch_bounds__(256) offsets_kernel(const int* __restrict__ skey, int64_t n, int K,
                                                       int* __restrict__ offsets) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 9);
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p > n) return;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(256) offsets_kernel(const int* __restrict__ sk
 
 __global__ void __launch_bounds__(CS_THREADS) csort_hist_kernel(const int64_t* __restrict__ bmu, int64_t n, int K, int per,
                                                                 int* __restrict__ hist) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 8);
     extern __shared__ int cs_bins[];
     for (int k = threadIdx.x; k < K; k += CS_THREADS) cs_bins[k] = 0;
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(CS_THREADS) csort_hist_kernel(const int64_t* _
 }
 
 __global__ void __launch_bounds__(256) csort_prefix_kernel(int* __restrict__ hist, int nb, int K, int* __restrict__ total) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 20);
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k >= K) return;
@@ -175,6 +179,7 @@ __global__ void __launch_bounds__(256) csort_prefix_kernel(int* __restrict__ his
 // one SM pays a wavefront per touched sector, a thread-owns-16-consecutive-keys layout cost 15 us here), all loaded up
 // front; warp scans of the 16 rows run side by side, then one scan over the 512 (row, warp) sums in key order
 __global__ void __launch_bounds__(1024) csort_offsets_kernel(const int* __restrict__ total, int K, int* __restrict__ offsets) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 21);
     constexpr int PER = CS_KMAX / 1024;
     __shared__ int row_warp_s[PER * 32];
@@ -239,6 +244,7 @@ __global__ void __launch_bounds__(CS_THREADS) csort_scatter_kernel(const int64_t
                                                                    const int* __restrict__ hist,
                                                                    const int* __restrict__ offsets,
                                                                    int* __restrict__ skey, int* __restrict__ sid) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 22);
     extern __shared__ int cs_bins[];                        // patches of the block seen so far, per key
     for (int k = threadIdx.x; k < K; k += CS_THREADS) cs_bins[k] = 0;
@@ -309,13 +315,39 @@ __device__ __forceinline__ void store_vec(float* p, const float (&r)[VEC]) {
     *reinterpret_cast<T*>(p) = t;
 }
 
+// positions per cp.async group of seg_level1_kernel: two groups of G rows + G W~ rows per warp in shared memory
+// (8 KB per warp, 64 KB per CTA, three CTAs per SM)
+template <int VEC> struct L1_GROUP { static constexpr int value = (VEC == 4) ? 4 : 8; };
+
+template <int VEC, bool STREAM>
+__device__ __forceinline__ void cp_async_vec(float* smem_dst, const float* src) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (VEC == 4) {
+        if (STREAM) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else if (VEC == 2) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    }
+}
 template <int VEC>
-__global__ void __launch_bounds__(ACC_WARPS * 32, VEC == 4 ? 2 : 3)
+__device__ __forceinline__ void lds_vec(float (&r)[VEC], const float* smem_src) {
+    using T = typename VecT<VEC>::T;
+    const T t = *reinterpret_cast<const T*>(smem_src);
+    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r[i] = f[i];
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(ACC_WARPS * 32, 3)
 seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ skey,
                   const int* __restrict__ sid, const int* __restrict__ offsets,
                   const float* __restrict__ Wt, float* __restrict__ Rbar,
                   float* __restrict__ partial, double* __restrict__ sse_part,
                   int S, int64_t n_chunks, int n_slices) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 10);
     const int lane = threadIdx.x & 31;
     const int64_t wg = blockIdx.x * (int64_t)ACC_WARPS + (threadIdx.x >> 5);
@@ -353,58 +385,97 @@ seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ s
         }
     };
 
-    // (key, patch base) of a group of 8 sorted positions: fetched by lanes 0..7 one group AHEAD of the rows they address
-    auto fetch = [&](int64_t p, int& k, int64_t& b) {
+    // Rows land in SHARED memory through cp.async, not in registers: every lane owns private words of a two-group ring
+    // (its slice of G patch rows and of their units' W~ rows per group), so no synchronisation is needed, and group
+    // g + 1 is on its way while group g is consumed.
+    // The kernel is bound by instruction issue, not by memory (ncu, 2^20 patches: 71 warp instructions per position,
+    // long-scoreboard stalls negligible), so everything per position that can be decided per GROUP is: lanes 0..G-1
+    // hold (key, patch base) of the group's positions, and two ballots turn "position valid" and "a new unit starts
+    // here" into warp-uniform bit masks.  The common position then costs one shuffle + one cp.async to issue and one
+    // shared load + the arithmetic to consume; keys are shuffled, W~ rows fetched and segments flushed only at the
+    // set bits (and W~ once per group, whose ring slot is recycled).
+    constexpr int G = L1_GROUP<VEC>::value;
+    constexpr unsigned GMASK = (1u << G) - 1u;
+    extern __shared__ __align__(16) float l1_ring[];     // [warp][buffer][row | W~][position][lane slice]
+    float (*mine)[2][G][32 * VEC] = reinterpret_cast<float (*)[2][G][32 * VEC]>(l1_ring) + (threadIdx.x >> 5) * 2;
+    const bool wide = n * (int64_t)D >= (1ll << 30);      // element offsets of x may not fit 32 bits: shuffle both halves
+    // group at p: (key, patch base) in lanes 0..G-1, masks of the valid positions and of those where the key differs
+    // from the position before (last_key: the key just before the group, -1 at the chunk start = always a start)
+    auto fetch = [&](int64_t p, int last_key, int& k, int64_t& b, unsigned& valid, unsigned& starts) {
         k = -1;
         b = 0;
-        if (lane < 8 && p + lane < p1) {
+        if (lane < G && p + lane < p1) {
             k = skey[p + lane];
             b = patch_base(g, (int64_t)sid[p + lane]);
         }
+        int before = __shfl_up_sync(0xffffffffu, k, 1);
+        if (lane == 0) before = last_key;
+        valid = __ballot_sync(0xffffffffu, k >= 0) & GMASK;
+        starts = __ballot_sync(0xffffffffu, k >= 0 && k != before) & GMASK;
     };
-    int my_key;
-    int64_t my_base;
-    fetch(p0, my_key, my_base);
-    for (int64_t p = p0; p < p1; p += 8) {
-        float row[8][VEC], wtr[8][VEC];
-        int key[8];
+    auto issue = [&](int buf, int k_l, int64_t b_l, unsigned valid, unsigned starts) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            key[u] = __shfl_sync(0xffffffffu, my_key, u);
-            int64_t base = __shfl_sync(0xffffffffu, my_base, u);
-            if (key[u] >= 0 && act) {
-                load_vec<VEC>(row[u], x + base + doff);
-                // the unit's W~ row travels with the patch row (L2-resident): no dependent load at a segment change
-                if (Wt != nullptr) load_vec<VEC>(wtr[u], Wt + (int64_t)key[u] * D + d);
-            } else {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) { row[u][i] = 0.f; wtr[u][i] = 0.f; }
+        for (int u = 0; u < G; ++u) {
+            if (!((valid >> u) & 1u)) break;              // warp-uniform
+            int64_t base = (int64_t)(uint32_t)__shfl_sync(0xffffffffu, (int)(uint32_t)b_l, u);
+            if (wide) base |= (int64_t)__shfl_sync(0xffffffffu, (int)(b_l >> 32), u) << 32;
+            if (act) cp_async_vec<VEC, true>(&mine[buf][0][u][lane * VEC], x + base + doff);
+            if (Wt != nullptr && (u == 0 || ((starts >> u) & 1u))) {
+                const int k = __shfl_sync(0xffffffffu, k_l, u);
+                if (act) cp_async_vec<VEC, false>(&mine[buf][1][u][lane * VEC], Wt + (int64_t)k * D + d);
             }
         }
-        fetch(p + 8, my_key, my_base);                // next group's keys in flight while this one is consumed
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int key_cur, key_next;
+    int64_t base_cur, base_next;
+    unsigned valid_cur, valid_next, starts_cur, starts_next;
+    fetch(p0, -1, key_cur, base_cur, valid_cur, starts_cur);
+    issue(0, key_cur, base_cur, valid_cur, starts_cur);
+    fetch(p0 + G, __shfl_sync(0xffffffffu, key_cur, G - 1), key_next, base_next, valid_next, starts_next);
+    int buf = 0;
+    float wtr[VEC];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (key[u] < 0) break;                    // warp-uniform: past the chunk end
-            if (key[u] != cur) {
+    for (int i = 0; i < VEC; ++i) wtr[i] = 0.f;
+    for (int64_t p = p0; p < p1; p += G) {
+        issue(buf ^ 1, key_next, base_next, valid_next, starts_next);      // (an empty group past the chunk end commits nothing)
+        const int key_mine = key_cur;
+        const unsigned valid_mine = valid_cur, starts_mine = starts_cur;
+        key_cur = key_next; base_cur = base_next; valid_cur = valid_next; starts_cur = starts_next;
+        // keys two groups ahead: in flight while this group is consumed
+        fetch(p + 2 * G, __shfl_sync(0xffffffffu, key_cur, G - 1), key_next, base_next, valid_next, starts_next);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            if (!((valid_mine >> u) & 1u)) break;         // warp-uniform: past the chunk end
+            const bool st = (starts_mine >> u) & 1u;
+            if (st) {
                 flush(p + u);
-                cur = key[u];
+                cur = __shfl_sync(0xffffffffu, key_mine, u);
                 run_start = p + u;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
             }
-            if (Wt != nullptr) {
+            if (act) {
+                float row[VEC];
+                lds_vec<VEC>(row, &mine[buf][0][u][lane * VEC]);
+                if (Wt != nullptr) {
+                    if (u == 0 || st) lds_vec<VEC>(wtr, &mine[buf][1][u][lane * VEC]);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    float r = wtr[u][i] - row[u][i];
-                    acc[i] += r;
-                    sse = fmaf(r, r, sse);
+                    for (int i = 0; i < VEC; ++i) {
+                        float r = wtr[i] - row[i];
+                        acc[i] += r;
+                        sse = fmaf(r, r, sse);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[i] += row[i];
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[i] += row[u][i];
             }
         }
+        buf ^= 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     flush(p1);
     if (sse_part != nullptr) {
         float t = warp_sum(act ? sse : 0.f);
@@ -417,6 +488,7 @@ __global__ void __launch_bounds__(ACC_WARPS * 32)
 seg_level2_kernel(const int* __restrict__ offsets, const float* __restrict__ partial,
                   float* __restrict__ Rbar, int64_t* __restrict__ counts, int K, int D, int S,
                   int n_slices) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 11);
     const int lane = threadIdx.x & 31;
     const int64_t wg = blockIdx.x * (int64_t)ACC_WARPS + (threadIdx.x >> 5);
@@ -468,6 +540,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 acc_scan_kernel(const float* __restrict__ x, Geom g, const int64_t* __restrict__ bmu, int K,
                 const float* __restrict__ Wt, float* __restrict__ Rbar, int64_t* __restrict__ counts,
                 double* __restrict__ sse_part, int n_slices) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 10);
     __shared__ int list[SCAN_CH];
     __shared__ int n_list;
@@ -565,6 +638,7 @@ acc_scan_kernel(const float* __restrict__ x, Geom g, const int64_t* __restrict__
 __global__ void __launch_bounds__(1024) sse_reduce_kernel(const double* __restrict__ part, int64_t m,
                                                           double* __restrict__ out, float* __restrict__ tail,
                                                           int64_t n_patches) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 12);
     __shared__ double sh[1024];
     double s = 0.0;
@@ -596,7 +670,15 @@ static int launch_levels(const float* x, const Geom& g, const AccumPlan& pl, con
     if (pl.n_chunks > 0) {
         int64_t warps = pl.n_chunks * n_slices;
         unsigned blocks = (unsigned)ceil_div64(warps, ACC_WARPS);
-        seg_level1_kernel<VEC><<<blocks, ACC_WARPS * 32, 0, st>>>(
+        constexpr size_t ring_bytes = (size_t)ACC_WARPS * 2 * 2 * L1_GROUP<VEC>::value * 32 * VEC * sizeof(float);
+        static PerDeviceFlag attr_done;
+        if (attr_done.pending()) {
+            cudaError_t e = cudaFuncSetAttribute(seg_level1_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)ring_bytes);
+            if (e != cudaSuccess) { set_error("accumulate: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
+            attr_done.set();
+        }
+        launch_pdl(seg_level1_kernel<VEC>, blocks, ACC_WARPS * 32, ring_bytes, st, 
             x, g, skey, sid, offsets, Wt, Rbar, partial, ((sse || tail) && Wt) ? sse_part : nullptr,
             pl.S, pl.n_chunks, n_slices);
         int rc = check_launch("seg_level1_kernel");
@@ -605,14 +687,14 @@ static int launch_levels(const float* x, const Geom& g, const AccumPlan& pl, con
     {
         int64_t warps = (int64_t)pl.K * n_slices;
         unsigned blocks = (unsigned)ceil_div64(warps, ACC_WARPS);
-        seg_level2_kernel<VEC><<<blocks, ACC_WARPS * 32, 0, st>>>(offsets, partial, Rbar, counts,
+        launch_pdl(seg_level2_kernel<VEC>, blocks, ACC_WARPS * 32, 0, st, offsets, partial, Rbar, counts,
                                                                  pl.K, g.D, pl.S, n_slices);
         int rc = check_launch("seg_level2_kernel");
         if (rc) return rc;
     }
     if (sse != nullptr || tail != nullptr) {
         int64_t m = (Wt != nullptr) ? pl.n_chunks * n_slices : 0;
-        sse_reduce_kernel<<<1, 1024, 0, st>>>(sse_part, m, sse, tail, g.n_patches);
+        launch_pdl(sse_reduce_kernel, 1, 1024, 0, st, sse_part, m, sse, tail, g.n_patches);
         return check_launch("sse_reduce_kernel");
     }
     return SOM_OK;
@@ -666,13 +748,13 @@ static int accumulate_impl(const float* x, int64_t n_img, int C, int H, int Wd, 
         const int n_slices = (int)ceil_div64(g.D, (int64_t)SCAN_THREADS * vec);
         dim3 grid((unsigned)K, (unsigned)n_slices);
         double* sp = ((sse || tail) && Wt) ? sse_part : nullptr;
-        if (vec == 4) acc_scan_kernel<4><<<grid, SCAN_THREADS, 0, st>>>(x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
-        else if (vec == 2) acc_scan_kernel<2><<<grid, SCAN_THREADS, 0, st>>>(x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
-        else acc_scan_kernel<1><<<grid, SCAN_THREADS, 0, st>>>(x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
+        if (vec == 4) launch_pdl(acc_scan_kernel<4>, grid, SCAN_THREADS, 0, st, x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
+        else if (vec == 2) launch_pdl(acc_scan_kernel<2>, grid, SCAN_THREADS, 0, st, x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
+        else launch_pdl(acc_scan_kernel<1>, grid, SCAN_THREADS, 0, st, x, g, bmu, K, Wt, Rbar, counts, sp, n_slices);
         rc = check_launch("acc_scan_kernel");
         if (rc) return rc;
         if (sse != nullptr || tail != nullptr) {
-            sse_reduce_kernel<<<1, 1024, 0, st>>>(sse_part, (Wt != nullptr) ? (int64_t)K * n_slices : 0, sse, tail, n);
+            launch_pdl(sse_reduce_kernel, 1, 1024, 0, st, sse_part, (Wt != nullptr) ? (int64_t)K * n_slices : 0, sse, tail, n);
             return check_launch("sse_reduce_kernel");
         }
         return SOM_OK;
@@ -692,21 +774,21 @@ static int accumulate_impl(const float* x, int64_t n_img, int C, int H, int Wd, 
             if (e != cudaSuccess) { set_error("accumulate: smem opt-in: %s", cudaGetErrorString(e)); return (int)e; }
             attr_done.set();
         }
-        csort_hist_kernel<<<pl.cs_blocks, CS_THREADS, bins, st>>>(bmu, n, K, pl.cs_per, hist);
+        launch_pdl(csort_hist_kernel, pl.cs_blocks, CS_THREADS, bins, st, bmu, n, K, pl.cs_per, hist);
         rc = check_launch("csort_hist_kernel");
         if (rc) return rc;
-        csort_prefix_kernel<<<(unsigned)ceil_div64(K, 256), 256, 0, st>>>(hist, pl.cs_blocks, K, total);
+        launch_pdl(csort_prefix_kernel, (unsigned)ceil_div64(K, 256), 256, 0, st, hist, pl.cs_blocks, K, total);
         rc = check_launch("csort_prefix_kernel");
         if (rc) return rc;
-        csort_offsets_kernel<<<1, 1024, 0, st>>>(total, K, offsets);
+        launch_pdl(csort_offsets_kernel, 1, 1024, 0, st, total, K, offsets);
         rc = check_launch("csort_offsets_kernel");
         if (rc) return rc;
-        csort_scatter_kernel<<<pl.cs_blocks, CS_THREADS, bins, st>>>(bmu, n, K, pl.cs_per, hist, offsets, keys_a, vals_a);
+        launch_pdl(csort_scatter_kernel, pl.cs_blocks, CS_THREADS, bins, st, bmu, n, K, pl.cs_per, hist, offsets, keys_a, vals_a);
         rc = check_launch("csort_scatter_kernel");
         if (rc) return rc;
     } else {
     if (n > 0) {
-        pairs_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(bmu, n, K, keys_a, vals_a);
+        launch_pdl(pairs_kernel, (unsigned)ceil_div64(n, 256), 256, 0, st, bmu, n, K, keys_a, vals_a);
         rc = check_launch("pairs_kernel");
         if (rc) return rc;
         cub::DoubleBuffer<int> kb(keys_a, keys_b), vb(vals_a, vals_b);
@@ -716,7 +798,7 @@ static int accumulate_impl(const float* x, int64_t n_img, int C, int H, int Wd, 
         skey = kb.Current();
         sid = vb.Current();
     }
-    offsets_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, st>>>(skey, n, K, offsets);
+    launch_pdl(offsets_kernel, (unsigned)ceil_div64(n + 1, 256), 256, 0, st, skey, n, K, offsets);
     rc = check_launch("offsets_kernel");
     if (rc) return rc;
     }

@@ -108,7 +108,7 @@ __device__ long long g_prof16[8];             // CTA 0's MMA loop: cycles, tiles
 template <int CG, bool MERGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
-    trace_stamp(s_trace_buf, 7);
+    pdl_launch_dependents();            // (the wait on the operand-split kernel comes after the barrier / TMEM prologue)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int B_STAGE = B_BLK_BYTES / CG;       // this CTA's share of a 256-unit block
@@ -164,6 +164,8 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
     if (CG == 2) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
+    pdl_wait();
+    trace_stamp(s_trace_buf, 7);
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -528,6 +530,7 @@ bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 // An all-zero or non-finite codebook keeps both at 1.  One CTA over the K norms.
 __device__ __forceinline__ void scales_from_max_norm(float mn, float* out2);
 __global__ void __launch_bounds__(1024) cb_scale_l_kernel(const float* __restrict__ cn, int K, float* __restrict__ scale_out) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 6);
     __shared__ float sh[32];
     float mn = 0.f;
@@ -569,6 +572,7 @@ __global__ void __launch_bounds__(256) split_w_l16_kernel(const float* __restric
                                                           int K, int D, int DB, int K_pad,
                                                           float* __restrict__ scale, __half* __restrict__ Bp,
                                                           __half* __restrict__ Tp) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 6);
     __shared__ float sh_max[8];
     __shared__ float sh_scale[2];
@@ -682,12 +686,12 @@ int launch_bmu_tc_l16(const float* x, const Geom& g, const float* W, const float
         const int64_t items = (int64_t)pl.K_pad * pl.DB * 32;
         const unsigned blocks = (unsigned)ceil_div64(items, 256);
         if (K <= 32768) {
-            split_w_l16_kernel<true><<<blocks, 256, 0, st>>>(W, cn, K, g.D, pl.DB, pl.K_pad, scale, Bp, Tp);
+            launch_pdl(split_w_l16_kernel<true>, blocks, 256, 0, st, W, cn, K, g.D, pl.DB, pl.K_pad, scale, Bp, Tp);
         } else {
-            cb_scale_l_kernel<<<1, 1024, 0, st>>>(cn, K, scale);
+            launch_pdl(cb_scale_l_kernel, 1, 1024, 0, st, cn, K, scale);
             rc = check_launch("cb_scale_l_kernel");
             if (rc) return rc;
-            split_w_l16_kernel<false><<<blocks, 256, 0, st>>>(W, cn, K, g.D, pl.DB, pl.K_pad, scale, Bp, Tp);
+            launch_pdl(split_w_l16_kernel<false>, blocks, 256, 0, st, W, cn, K, g.D, pl.DB, pl.K_pad, scale, Bp, Tp);
         }
         rc = check_launch("split_w_l16_kernel");
         if (rc) return rc;
@@ -725,13 +729,15 @@ int launch_bmu_tc_l16(const float* x, const Geom& g, const float* W, const float
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)pl.cg;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // (see som_common.cuh: pdl_begin)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t le = cudaLaunchKernelEx(&cfg, kernels[2 * pl.merged + pl.cg - 1], map_b, map_t, P);
     if (le != cudaSuccess) { set_error("bmu_tc_l16_kernel: launch: %s", cudaGetErrorString(le)); return (int)le; }
     return check_launch("bmu_tc_l16_kernel");

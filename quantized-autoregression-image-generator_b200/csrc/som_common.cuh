@@ -86,6 +86,38 @@ __device__ __forceinline__ void trace_stamp(unsigned long long* buf, int id) {
     static __device__ unsigned long long* s_trace_buf = nullptr;                        \
     void setter(unsigned long long* p) { cudaMemcpyToSymbol(s_trace_buf, &p, sizeof(p)); }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------
+// The training step is a chain of ~20 short dependent kernels; replayed from a CUDA graph each link still cost ~1.8 us
+// between the last block of one kernel and the first block of the next (device-timestamp trace).  Kernels on that chain
+// are launched with the programmatic-stream-serialization attribute and begin with pdl_begin(): they let THEIR successor
+// become resident at once, then block until the predecessor has completed and flushed.  Rules that keep this safe:
+// every chained kernel executes the wait before its first global access and before it exits (completion is then
+// transitive along the chain), and nothing before the wait touches global memory.
+#ifdef SOM_PDL_EARLY_TRIGGER
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#endif
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_begin() { pdl_launch_dependents(); pdl_wait(); }
+
+bool pdl_enabled();                                   // som_core.cu; som_debug_set_pdl(0) turns the attribute off (A/B timing)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

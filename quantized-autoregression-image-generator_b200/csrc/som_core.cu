@@ -89,6 +89,7 @@ int make_geom(Geom* g, const void* x, int64_t n_img, int C, int H, int W, int pH
 template <int G, int U, int J>
 __global__ void __launch_bounds__(256) norm2_kernel(const float* __restrict__ W, int K, int D,
                                                     float* __restrict__ out) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 5);
     constexpr int RPW = (32 / G) * U;                       // units per warp per iteration
     const int lane = threadIdx.x & (G - 1);
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) norm2_kernel(const float* __restrict__ W,
 // order (four loads in flight), then a warp butterfly and the eight warp sums in warp order: fixed order, and the
 // rule depends on D only, so a unit's norm does not depend on how many units the launch (or the shard) holds.
 __global__ void __launch_bounds__(256) norm2_long_kernel(const float* __restrict__ W, int D, float* __restrict__ out) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 5);
     __shared__ float part[8];
     const float* row = W + (int64_t)blockIdx.x * D;
@@ -475,6 +477,7 @@ __device__ __forceinline__ void adam_body(float* __restrict__ W, float* __restri
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ W, float* __restrict__ m,
                                                    float* __restrict__ v, const float* __restrict__ g,
                                                    int64_t n, AdamScalars a) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 19);
     adam_body(W, m, v, g, n, a);
 }
@@ -485,6 +488,7 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ W, fl
                                                        float* __restrict__ v, const float* __restrict__ g,
                                                        int64_t n, double lr, double b1, double b2, float eps,
                                                        const int64_t* __restrict__ steps_done) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 19);
     const double t = (double)(*steps_done + 1);
     AdamScalars a;
@@ -505,6 +509,7 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(float* __restrict__ W, flo
                                                       int64_t n, int D, double lr, double b1, double b2, float eps,
                                                       int64_t* __restrict__ steps_done,
                                                       const float* __restrict__ tail, double* __restrict__ loss_out) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 18);
     const double t = (double)(steps_done[0] + 1);
     const double numel = ((double)tail[2] * 4096.0 + (double)tail[3]) * (double)D;
@@ -607,6 +612,13 @@ void trace_set_accumulate(unsigned long long*);
 void trace_set_peer(unsigned long long*);
 }  // namespace som
 
+namespace som {
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+}
+// debug: programmatic dependent launch on the step's kernel chain (default on); 0 = plain stream order, for A/B timing
+extern "C" SOM_API void som_debug_set_pdl(int on) { som::g_pdl = on; }
+
 // debug: hand every translation unit the trace buffer (8 KB + 64 KB of device memory, zero-filled; NULL switches it off)
 extern "C" SOM_API int som_debug_trace(unsigned long long* buf) {
     som::trace_set_core(buf); som::trace_set_filter_tc(buf); som::trace_set_filter(buf); som::trace_set_l16(buf);
@@ -640,18 +652,18 @@ int som_prepare_codebook_f32(const float* W, int K, int D, float* c_norm2, void*
     SOM_REQUIRE(K > 0 && D > 0, SOM_E_BADARG, "prepare_codebook: K=%d D=%d", K, D);
     cudaStream_t st = (cudaStream_t)stream;
     if (D >= 2048) {
-        norm2_long_kernel<<<(unsigned)K, 256, 0, st>>>(W, D, c_norm2);
+        launch_pdl(norm2_long_kernel, (unsigned)K, 256, 0, st, W, D, c_norm2);
         return check_launch("norm2_long_kernel");
     }
     if (D > 16) {            // 4 units x 4 row segments in flight per lane
         int blocks = grid_for(ceil_div64(K, 4) * 32, 256, 8);
-        norm2_kernel<32, 4, 4><<<blocks, 256, 0, st>>>(W, K, D, c_norm2);
+        launch_pdl(norm2_kernel<32, 4, 4>, blocks, 256, 0, st, W, K, D, c_norm2);
     } else if (D > 8) {      // 2 x 8 units per warp
         int blocks = grid_for(ceil_div64(K, 16) * 32, 256, 8);
-        norm2_kernel<16, 8, 1><<<blocks, 256, 0, st>>>(W, K, D, c_norm2);
+        launch_pdl(norm2_kernel<16, 8, 1>, blocks, 256, 0, st, W, K, D, c_norm2);
     } else {                 // 4 x 8 units per warp
         int blocks = grid_for(ceil_div64(K, 32) * 32, 256, 8);
-        norm2_kernel<8, 8, 1><<<blocks, 256, 0, st>>>(W, K, D, c_norm2);
+        launch_pdl(norm2_kernel<8, 8, 1>, blocks, 256, 0, st, W, K, D, c_norm2);
     }
     return check_launch("norm2_kernel");
 }
@@ -773,7 +785,7 @@ int som_adam_f32(float* W, float* m, float* v, const float* g, int64_t n,
     double bc2_sqrt = sqrt(bc2);
     int blocks = grid_for(n, 256 * 4, 8);
     AdamScalars a{(float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)step_size, (float)bc2_sqrt, (float)eps};
-    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, m, v, g, n, a);
+    launch_pdl(adam_kernel, blocks, 256, 0, (cudaStream_t)stream, W, m, v, g, n, a);
     return check_launch("adam_kernel");
 }
 
@@ -783,7 +795,7 @@ int som_adam_devstep_f32(float* W, float* m, float* v, const float* g, int64_t n
     SOM_REQUIRE(n >= 0, SOM_E_BADARG, "adam(devstep): n=%lld", (long long)n);
     if (n > 0) {
         int blocks = grid_for(n, 256 * 4, 8);
-        adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, m, v, g, n, lr, b1, b2, (float)eps, steps_done);
+        launch_pdl(adam_dev_kernel, blocks, 256, 0, (cudaStream_t)stream, W, m, v, g, n, lr, b1, b2, (float)eps, steps_done);
         int rc = check_launch("adam_dev_kernel");
         if (rc) return rc;
     }
@@ -798,7 +810,7 @@ int som_adam_dp_f32(float* W, float* m, float* v, const float* g, int64_t n, int
     SOM_REQUIRE(n >= 0 && D > 0, SOM_E_BADARG, "adam(dp): n=%lld D=%d", (long long)n, D);
     if (n > 0) {
         int blocks = grid_for(n, 256 * 4, 8);
-        adam_dp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, m, v, g, n, D, lr, b1, b2, (float)eps, steps_done,
+        launch_pdl(adam_dp_kernel, blocks, 256, 0, (cudaStream_t)stream, W, m, v, g, n, D, lr, b1, b2, (float)eps, steps_done,
                                                                 tail, loss_out);
         return check_launch("adam_dp_kernel");
     }

@@ -25,6 +25,7 @@ constexpr int FILT_PAD = FILT_TA + 8;
 __global__ void __launch_bounds__(FILT_WARPS * 32)
 filter_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int D,
               float two_var, int h, float scale) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 4);
     extern __shared__ float tab[];
     const int off = h + FILT_PAD;
@@ -104,6 +105,7 @@ template <int TD, int JS>
 __global__ void __launch_bounds__(FT_THREADS)
 filter_tile_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int D,
                    float two_var, int h, float scale) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 4);
     constexpr int FG = TD / 4;                     // feature groups (threads) per row
     constexpr int UG = FT_THREADS / (FG * JS);     // unit groups per CTA
@@ -306,11 +308,11 @@ extern "C" int som_filter_f32(const float* in, float* out, int K, int D,
             attr_t.set();
         }
         dim3 gt((unsigned)ceil_div64(K, 32), (unsigned)ceil_div64(D, td));      // 32 units per CTA in both shapes
-        if (td == 128) filter_tile_kernel<128, 2><<<gt, FT_THREADS, smem_t, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);
-        else filter_tile_kernel<64, 4><<<gt, FT_THREADS, smem_t, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);
+        if (td == 128) launch_pdl(filter_tile_kernel<128, 2>, gt, FT_THREADS, smem_t, (cudaStream_t)stream, in, out, K, D, two_var, h, scale);
+        else launch_pdl(filter_tile_kernel<64, 4>, gt, FT_THREADS, smem_t, (cudaStream_t)stream, in, out, K, D, two_var, h, scale);
         return check_launch("filter_tile_kernel");
     }
     dim3 grid((unsigned)ceil_div64(K, FILT_WARPS * FILT_TA), (unsigned)ceil_div64(D, 32));
-    filter_kernel<<<grid, FILT_WARPS * 32, smem, (cudaStream_t)stream>>>(in, out, K, D, two_var, h, scale);
+    launch_pdl(filter_kernel, grid, FILT_WARPS * 32, smem, (cudaStream_t)stream, in, out, K, D, two_var, h, scale);
     return check_launch("filter_kernel");
 }

@@ -74,6 +74,7 @@ __device__ __forceinline__ void mma_tf32_n(uint32_t tmem_d, uint64_t adesc, uint
 // memory: reads coalesced along d, writes coalesced along j.
 __global__ void __launch_bounds__(256) split_in_t_kernel(const float* __restrict__ in, int K, int D, int h, int Kp,
                                                          float* __restrict__ Bhi, float* __restrict__ Blo) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 1);
     __shared__ float tile[32][33];
     const int jp0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -100,7 +101,7 @@ template <int TNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                  const Params P) {
-    trace_stamp(s_trace_buf, 2);
+    pdl_launch_dependents();            // (the wait comes after the barrier / weight-table / TMEM prologue)
     constexpr int STAGE = stage_bytes<TNF>();
     constexpr int B_BYTES = TNF * KBLK * 4;
     extern __shared__ uint8_t smem_raw[];
@@ -147,6 +148,8 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
     const int nkb = P.nkb;
+    pdl_wait();
+    trace_stamp(s_trace_buf, 2);
 
     if (warp == 0) {
         // ================================ TMA producer (B blocks) ================================
@@ -274,6 +277,7 @@ done:
 // out = scale * (((p0 + p1) + p2) + p3): the unsplit epilogue's order
 __global__ void __launch_bounds__(256) filter_reduce_kernel(const float* __restrict__ partial, int64_t n, float scale,
                                                             float* __restrict__ out) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 3);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -347,7 +351,7 @@ int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, i
     float* Blo = (float*)((char*)ws + pl.off_lo);
     {
         dim3 grid((unsigned)(pl.Kp / 32), (unsigned)ceil_div64(D, 32));
-        split_in_t_kernel<<<grid, 256, 0, st>>>(in, K, D, h, pl.Kp, Bhi, Blo);
+        launch_pdl(split_in_t_kernel, grid, 256, 0, st, in, K, D, h, pl.Kp, Bhi, Blo);
         int rc = check_launch("split_in_t_kernel");
         if (rc) return rc;
     }
@@ -371,14 +375,14 @@ int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, i
         attr_done.set();
     }
     dim3 grid((unsigned)ceil_div64(K, TMU), (unsigned)ceil_div64(D, pl.tnf), (unsigned)pl.ks);
-    if (pl.tnf == 128) filter_tc_kernel<128><<<grid, NUM_THREADS, smem, st>>>(map_bhi, map_blo, P);
-    else filter_tc_kernel<64><<<grid, NUM_THREADS, smem, st>>>(map_bhi, map_blo, P);
+    if (pl.tnf == 128) launch_pdl(filter_tc_kernel<128>, grid, NUM_THREADS, smem, st, map_bhi, map_blo, P);
+    else launch_pdl(filter_tc_kernel<64>, grid, NUM_THREADS, smem, st, map_bhi, map_blo, P);
     rc = check_launch("filter_tc_kernel");
     if (rc || pl.ks == 1) return rc;
     const int64_t n = (int64_t)K * D;
     int blocks = (int)ceil_div64(n, 256 * 4);
     if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-    filter_reduce_kernel<<<blocks, 256, 0, st>>>(P.partial, n, scale, out);
+    launch_pdl(filter_reduce_kernel, blocks, 256, 0, st, P.partial, n, scale, out);
     return check_launch("filter_reduce_kernel");
 }
 

@@ -79,6 +79,7 @@ __device__ __forceinline__ bool grid_sync_ranks(const Pads& pads, uint32_t* coun
 
 // one-block barrier over the ranks: everything this rank enqueued before it is visible to the peers' later kernels
 __global__ void __launch_bounds__(32) barrier_kernel(Pads pads, int channel, int rank, int world) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 13);
     if ((int)threadIdx.x < world) {
         __threadfence_system();
@@ -132,6 +133,7 @@ __device__ __forceinline__ float4 exact_tail(const Pads& bufs, int64_t q_tail, i
 __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q0, int64_t q1, int64_t q_tail,
                                                             float4* __restrict__ tail_out, Pads bufs, Pads pads,
                                                             uint32_t* counter, int channel, int rank, int world) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 17);
     // (barrier_kernel ran before this launch: every rank's input is complete)
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(THREADS) allreduce_kernel(float* mc, int64_t q
 __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(const float* mc, int64_t q0, int64_t q1, int64_t q_tail,
                                                               float4* __restrict__ out, float4* __restrict__ tail_out,
                                                               Pads bufs, int world) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 14);
     // (barrier_kernel ran before this launch: every rank's accumulators are complete)
     const int64_t stride = (int64_t)gridDim.x * THREADS;
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(const float* mc, i
 // local rows -> the same rows of every rank (multicast store), then the cross-rank barrier that makes them visible
 __global__ void __launch_bounds__(THREADS) bcast_rows_kernel(const float4* __restrict__ src, float* mc_dst, int64_t n4,
                                                              Pads pads, uint32_t* counter, int channel, int rank, int world) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 16);
     const int64_t stride = (int64_t)gridDim.x * THREADS;
     for (int64_t q = blockIdx.x * (int64_t)THREADS + threadIdx.x; q < n4; q += stride) mm_st(mc_dst + 4 * q, src[q]);
@@ -202,6 +206,7 @@ __global__ void __launch_bounds__(THREADS) adam_slice_bcast_kernel(const float4*
                                                                    const float* __restrict__ tail,
                                                                    double* __restrict__ loss_out, Pads pads,
                                                                    uint32_t* counter, int channel, int rank, int world) {
+    pdl_begin();
     trace_stamp(s_trace_buf, 15);
     const double t = (double)(steps_done[0] + 1);
     const double numel = ((double)tail[2] * 4096.0 + (double)tail[3]) * (double)D;
@@ -239,7 +244,7 @@ static int make_pads(Pads* pads, void* const* signal_pads, int rank, int world) 
 // words [64, 68) = the local block-arrival counters of the four channels
 static uint32_t* counter_of(const Pads& pads, int rank, int channel) { return pads.p[rank] + 64 + channel; }
 static int launch_barrier(const Pads& pads, int channel, int rank, int world, cudaStream_t st) {
-    barrier_kernel<<<1, 32, 0, st>>>(pads, channel, rank, world);
+    launch_pdl(barrier_kernel, 1, 32, 0, st, pads, channel, rank, world);
     return check_launch("peer_barrier_kernel");
 }
 // One quad per thread while that stays within two blocks per SM: these kernels are latency-bound (a multimem load or a
@@ -280,7 +285,7 @@ extern "C" int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer
     const int64_t q0 = per * rank < n4 ? per * rank : n4, q1 = q0 + per < n4 ? q0 + per : n4;
     rc = launch_barrier(pads, channel, rank, world, (cudaStream_t)stream);
     if (rc) return rc;
-    allreduce_kernel<<<grid_for(per), THREADS, 0, (cudaStream_t)stream>>>(
+    launch_pdl(allreduce_kernel, grid_for(per), THREADS, 0, (cudaStream_t)stream, 
         (float*)mc_buf, q0, q1, q_tail, tail_out, bufs, pads, counter_of(pads, rank, channel), channel, rank, world);
     return check_launch("peer_allreduce_kernel");
 }
@@ -304,7 +309,7 @@ extern "C" int som_peer_reduce_rows_f32(const void* mc_packed, void* const* peer
     rc = launch_barrier(pads, channel, rank, world, (cudaStream_t)stream);
     if (rc) return rc;
     (void)max_rows;
-    reduce_rows_kernel<<<grid_for((int64_t)(row1 - row0) * d4), THREADS, 0, (cudaStream_t)stream>>>(
+    launch_pdl(reduce_rows_kernel, grid_for((int64_t)(row1 - row0) * d4), THREADS, 0, (cudaStream_t)stream, 
         (const float*)mc_packed, (int64_t)row0 * d4, (int64_t)row1 * d4, (int64_t)K * d4, (float4*)out_rows,
         (float4*)out_tail, bufs, world);
     return check_launch("peer_reduce_rows_kernel");
@@ -321,7 +326,7 @@ extern "C" int som_peer_bcast_rows_f32(const float* src_rows, void* mc_dst_rows,
     int rc = make_pads(&pads, signal_pads, rank, world);
     if (rc) return rc;
     (void)max_n;
-    bcast_rows_kernel<<<grid_for(n / 4), THREADS, 0, (cudaStream_t)stream>>>((const float4*)src_rows, (float*)mc_dst_rows,
+    launch_pdl(bcast_rows_kernel, grid_for(n / 4), THREADS, 0, (cudaStream_t)stream, (const float4*)src_rows, (float*)mc_dst_rows,
                                                                            n / 4, pads, counter_of(pads, rank, channel),
                                                                            channel, rank, world);
     return check_launch("peer_bcast_rows_kernel");
@@ -341,7 +346,7 @@ extern "C" int som_peer_adam_slice_f32(const float* W_rows, void* mc_W_rows, flo
     int rc = make_pads(&pads, signal_pads, rank, world);
     if (rc) return rc;
     (void)max_n;
-    adam_slice_bcast_kernel<<<grid_for(n / 4), THREADS, 0, (cudaStream_t)stream>>>(
+    launch_pdl(adam_slice_bcast_kernel, grid_for(n / 4), THREADS, 0, (cudaStream_t)stream, 
         (const float4*)W_rows, (float*)mc_W_rows, (float4*)m_rows, (float4*)v_rows, (const float4*)g_rows, n / 4, D, lr, b1,
         b2, (float)eps, steps_done, tail, loss_out, pads, counter_of(pads, rank, channel), channel, rank, world);
     return check_launch("peer_adam_slice_bcast_kernel");

@@ -155,6 +155,33 @@ def test_accumulate_small_and_medium_batches(fmaps, k):
     assert torch.equal(rbar, rbar2) and torch.equal(sse, sse2)
 
 
+@pytest.mark.parametrize("fmaps,k,skew", [(128, 16384, False), (2048, 16384, False), (2500, 16384, True), (515, 5000, True),
+                                          (4096, 300, True)])
+def test_accumulate_counting_sort_equals_radix_sort_path(fmaps, k, skew):
+    """Codebooks of up to 16 384 units sort the (unit, patch) pairs with the library's own one-pass stable counting sort,
+    larger ones with cub's radix sort.  Both are stable, so the segmented sums must be BIT-identical: the same hits are
+    accumulated once with K units and once with K + 16 385 units (the extra units stay empty and push the call onto
+    the radix path).  Covers several sort blocks, more than one block per SM's worth of patches, and a heavy hitter."""
+    pd = (4, 4)
+    x = synthetic_fmaps(fmaps, 901 + fmaps).to(DEV)
+    geom = ops.geometry(x.shape, pd)
+    n = ops.n_patches_of(geom)
+    g = torch.Generator().manual_seed(n + k)
+    bmu = torch.randint(0, k, (n,), generator=g)
+    if skew:
+        bmu[::2] = k - 1                                     # half of the batch on the last unit
+        bmu[1::64] = 0
+    k_big = k + 16385
+    table = torch.randn(k_big, 64, generator=g).to(DEV)
+    bmu = bmu.to(DEV)
+    small, c_small, sse_small = ops.accumulate(x, geom, bmu, table[:k].contiguous(), k, want_counts=True, want_sse=True)
+    big, c_big, sse_big = ops.accumulate(x, geom, bmu, table, k_big, want_counts=True, want_sse=True)
+    assert torch.equal(small, big[:k])
+    assert float(big[k:].abs().max()) == 0.0
+    assert torch.equal(c_small, c_big[:k]) and int(c_big[k:].sum()) == 0
+    assert torch.equal(sse_small, sse_big)
+
+
 def _teacher_force(monkeypatch, rec):
     """Make the drop-in module's BMU search return the reference's own indices (teacher forcing): from
     the reference's fresh init a near-tie may resolve differently, and the quantise / autograd outputs are only

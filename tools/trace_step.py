@@ -31,6 +31,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    lib = ctypes.CDLL(somcb._lib.LIB_PATH)
+    if os.environ.get("TRACE_PDL", "1") == "0":            # A/B: plain stream order between the step's kernels
+        lib.som_debug_set_pdl(0)
     lo, hi = somcb.shard_bounds(int(os.environ.get("TRACE_IMAGES", "16384")), world, rank)
     xs = [bench._fmaps(hi - lo, 5000 + 131 * b + rank, dev) for b in range(4)]
     cb = bench._codebook(16384, (4, 4), dev)
@@ -40,7 +43,6 @@ def main():
     for i in range(10):
         tr.step(xs[i % 4])
     torch.cuda.synchronize()
-    lib = ctypes.CDLL(somcb._lib.LIB_PATH)
     buf = torch.zeros(8200, dtype=torch.int64, device=dev)
     lib.som_debug_trace(ctypes.c_void_p(buf.data_ptr()))
     steps = 5
