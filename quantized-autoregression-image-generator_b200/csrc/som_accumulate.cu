@@ -247,8 +247,11 @@ __global__ void __launch_bounds__(CS_THREADS) csort_scatter_kernel(const int64_t
     pdl_begin();
     trace_stamp(s_trace_buf, 22);
     extern __shared__ int cs_bins[];                        // patches of the block seen so far, per key
+    __shared__ uint64_t turn_bar[CS_THREADS / 32];          // warp w may take its turn (one phase per round)
     for (int k = threadIdx.x; k < K; k += CS_THREADS) cs_bins[k] = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < CS_THREADS / 32)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&turn_bar[threadIdx.x])));
     const int* blk = hist + (int64_t)blockIdx.x * K;
     const int64_t p0 = (int64_t)blockIdx.x * per;
     auto key_of = [&](int64_t p) -> int {
@@ -258,12 +261,16 @@ __global__ void __launch_bounds__(CS_THREADS) csort_scatter_kernel(const int64_t
     };
     int key_next = key_of(p0 + threadIdx.x);
     __syncthreads();
+    const uint32_t my_bar = (uint32_t)__cvta_generic_to_shared(&turn_bar[warp]);
+    const uint32_t next_bar = (uint32_t)__cvta_generic_to_shared(&turn_bar[(warp + 1) & (CS_THREADS / 32 - 1)]);
+    if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(my_bar) : "memory");   // warp 0 starts
+    uint32_t round = 0;
 #pragma unroll 1
-    for (int u = 0; u < per; u += CS_THREADS) {
+    for (int u = 0; u < per; u += CS_THREADS, ++round) {
         const int64_t p = p0 + u + threadIdx.x;
         const int key = key_next;
         if (u + CS_THREADS < per) key_next = key_of(p + CS_THREADS);       // next round's keys fly during the turns
-        // where the block's patches of this key start: two gathers, needed only AFTER the turns (kept out of them --
+        // where the block's patches of this key start: two gathers, needed only AFTER the turn (kept out of it --
         // a first version let the compiler sink them into the turn and paid an L2 round trip per warp turn)
         int base = 0;
         if (key >= 0) base = offsets[key] + blk[key];
@@ -271,16 +278,24 @@ __global__ void __launch_bounds__(CS_THREADS) csort_scatter_kernel(const int64_t
         const unsigned grp = __match_any_sync(0xffffffffu, key);
         const int rank_in_warp = __popc(grp & ((1u << lane) - 1u));
         const int add = ((grp >> lane) == 1u) ? __popc(grp) : 0;
-        int local = 0;
-#pragma unroll 1
-        for (int w = 0; w < CS_THREADS / 32; ++w) {          // warps take turns: ascending patch order per key
-            if (warp == w) {                                 // (one full-warp sync: a sync per match group serialised them)
-                if (key >= 0) local = cs_bins[key];
-                __syncwarp();
-                if (add && key >= 0) cs_bins[key] = local + add;
-            }
-            __syncthreads();
+        // Warps take turns in warp order (ascending patch order per key), handing the turn on through one mbarrier per
+        // warp: the waiting warps sleep in try_wait instead of all 32 meeting in a block barrier per turn (a turn
+        // cost ~400 cycles that way, 224 turns per block at 2^20 patches).
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile(
+                    "{\n.reg .pred p;\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                    "selp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(done) : "r"(my_bar), "r"(round & 1u) : "memory");
         }
+        int local = 0;
+        if (key >= 0) local = cs_bins[key];
+        __syncwarp();                                        // (one full-warp sync: a sync per match group serialised them)
+        if (add && key >= 0) cs_bins[key] = local + add;
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(next_bar) : "memory");
         if (key >= 0) {
             const int pos = base + local + rank_in_warp;
             skey[pos] = key;
@@ -386,19 +401,24 @@ seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ s
     };
 
     // Rows land in SHARED memory through cp.async, not in registers: every lane owns private words of a two-group ring
-    // (its slice of G patch rows and of their units' W~ rows per group), so no synchronisation is needed, and group
-    // g + 1 is on its way while group g is consumed.
-    // The kernel is bound by instruction issue, not by memory (ncu, 2^20 patches: 71 warp instructions per position,
-    // long-scoreboard stalls negligible), so everything per position that can be decided per GROUP is: lanes 0..G-1
-    // hold (key, patch base) of the group's positions, and two ballots turn "position valid" and "a new unit starts
-    // here" into warp-uniform bit masks.  The common position then costs one shuffle + one cp.async to issue and one
-    // shared load + the arithmetic to consume; keys are shuffled, W~ rows fetched and segments flushed only at the
-    // set bits (and W~ once per group, whose ring slot is recycled).
+    // (its slice of G patch rows and of their units' W~ rows per group), so the rows need no synchronisation, and
+    // group g + 1 is on its way while group g is consumed.
+    // The kernel is bound by instruction issue, not by memory (ncu, 2^20 patches: 71, later 65 warp instructions per
+    // position, long-scoreboard stalls negligible), so everything per position that can be decided per GROUP is:
+    // lanes 0..G-1 fetch (key, patch base) of the group's positions, two ballots turn "position valid" and "a new unit
+    // starts here" into warp-wide bit masks, and the pairs go through a small shared table that every lane reads back
+    // with one broadcast load (a shuffle costs its divergence check as well).  A position then costs a table load, the
+    // address and one cp.async to issue, one shared load and the arithmetic to consume; W~ rows are fetched and
+    // segments flushed only at the set bits (W~ also once per group, whose ring slot is recycled).  Lanes past the
+    // row's end (D not a multiple of the slice) stream the slice of lane 0 and are never stored.
     constexpr int G = L1_GROUP<VEC>::value;
     constexpr unsigned GMASK = (1u << G) - 1u;
-    extern __shared__ __align__(16) float l1_ring[];     // [warp][buffer][row | W~][position][lane slice]
-    float (*mine)[2][G][32 * VEC] = reinterpret_cast<float (*)[2][G][32 * VEC]>(l1_ring) + (threadIdx.x >> 5) * 2;
-    const bool wide = n * (int64_t)D >= (1ll << 30);      // element offsets of x may not fit 32 bits: shuffle both halves
+    extern __shared__ __align__(16) float l1_ring[];     // [warp][buffer][row | W~][position][lane slice], then the tables
+    const int wib = threadIdx.x >> 5;
+    float (*mine)[2][G][32 * VEC] = reinterpret_cast<float (*)[2][G][32 * VEC]>(l1_ring) + wib * 2;
+    int4 (*tab)[G] = reinterpret_cast<int4 (*)[G]>(l1_ring + (size_t)ACC_WARPS * 2 * 2 * G * 32 * VEC) + wib * 2;
+    const float* x_lane = x + (act ? doff : 0);
+    const float* wt_lane = Wt + (act ? d : 0);
     // group at p: (key, patch base) in lanes 0..G-1, masks of the valid positions and of those where the key differs
     // from the position before (last_key: the key just before the group, -1 at the chunk start = always a start)
     auto fetch = [&](int64_t p, int last_key, int& k, int64_t& b, unsigned& valid, unsigned& starts) {
@@ -413,17 +433,20 @@ seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ s
         valid = __ballot_sync(0xffffffffu, k >= 0) & GMASK;
         starts = __ballot_sync(0xffffffffu, k >= 0 && k != before) & GMASK;
     };
-    auto issue = [&](int buf, int k_l, int64_t b_l, unsigned valid, unsigned starts) {
+    auto publish = [&](int buf, int k_l, int64_t b_l) {
+        __syncwarp();                                     // (the table's previous readers are done)
+        if (lane < G) tab[buf][lane] = make_int4((int)(uint32_t)b_l, (int)(b_l >> 32), k_l, 0);
+        __syncwarp();
+    };
+    auto issue = [&](int buf, unsigned valid, unsigned starts) {
 #pragma unroll
         for (int u = 0; u < G; ++u) {
-            if (!((valid >> u) & 1u)) break;              // warp-uniform
-            int64_t base = (int64_t)(uint32_t)__shfl_sync(0xffffffffu, (int)(uint32_t)b_l, u);
-            if (wide) base |= (int64_t)__shfl_sync(0xffffffffu, (int)(b_l >> 32), u) << 32;
-            if (act) cp_async_vec<VEC, true>(&mine[buf][0][u][lane * VEC], x + base + doff);
-            if (Wt != nullptr && (u == 0 || ((starts >> u) & 1u))) {
-                const int k = __shfl_sync(0xffffffffu, k_l, u);
-                if (act) cp_async_vec<VEC, false>(&mine[buf][1][u][lane * VEC], Wt + (int64_t)k * D + d);
-            }
+            if (valid != GMASK && !((valid >> u) & 1u)) break;       // (only the last group of the whole batch is short)
+            const int4 e = tab[buf][u];
+            const int64_t base = (int64_t)(((uint64_t)(uint32_t)e.y << 32) | (uint32_t)e.x);
+            cp_async_vec<VEC, true>(&mine[buf][0][u][lane * VEC], x_lane + base);
+            if (Wt != nullptr && (u == 0 || ((starts >> u) & 1u)))
+                cp_async_vec<VEC, false>(&mine[buf][1][u][lane * VEC], wt_lane + (int64_t)e.z * D);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -431,46 +454,45 @@ seg_level1_kernel(const float* __restrict__ x, Geom g, const int* __restrict__ s
     int64_t base_cur, base_next;
     unsigned valid_cur, valid_next, starts_cur, starts_next;
     fetch(p0, -1, key_cur, base_cur, valid_cur, starts_cur);
-    issue(0, key_cur, base_cur, valid_cur, starts_cur);
+    publish(0, key_cur, base_cur);
+    issue(0, valid_cur, starts_cur);
     fetch(p0 + G, __shfl_sync(0xffffffffu, key_cur, G - 1), key_next, base_next, valid_next, starts_next);
     int buf = 0;
     float wtr[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) wtr[i] = 0.f;
     for (int64_t p = p0; p < p1; p += G) {
-        issue(buf ^ 1, key_next, base_next, valid_next, starts_next);      // (an empty group past the chunk end commits nothing)
-        const int key_mine = key_cur;
+        publish(buf ^ 1, key_next, base_next);
+        issue(buf ^ 1, valid_next, starts_next);          // (an empty group past the chunk end commits nothing)
         const unsigned valid_mine = valid_cur, starts_mine = starts_cur;
-        key_cur = key_next; base_cur = base_next; valid_cur = valid_next; starts_cur = starts_next;
+        key_cur = key_next; valid_cur = valid_next; starts_cur = starts_next;
         // keys two groups ahead: in flight while this group is consumed
         fetch(p + 2 * G, __shfl_sync(0xffffffffu, key_cur, G - 1), key_next, base_next, valid_next, starts_next);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
 #pragma unroll
         for (int u = 0; u < G; ++u) {
-            if (!((valid_mine >> u) & 1u)) break;         // warp-uniform: past the chunk end
+            if (valid_mine != GMASK && !((valid_mine >> u) & 1u)) break;
             const bool st = (starts_mine >> u) & 1u;
             if (st) {
                 flush(p + u);
-                cur = __shfl_sync(0xffffffffu, key_mine, u);
+                cur = tab[buf][u].z;
                 run_start = p + u;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
             }
-            if (act) {
-                float row[VEC];
-                lds_vec<VEC>(row, &mine[buf][0][u][lane * VEC]);
-                if (Wt != nullptr) {
-                    if (u == 0 || st) lds_vec<VEC>(wtr, &mine[buf][1][u][lane * VEC]);
+            float row[VEC];
+            lds_vec<VEC>(row, &mine[buf][0][u][lane * VEC]);
+            if (Wt != nullptr) {
+                if (u == 0 || st) lds_vec<VEC>(wtr, &mine[buf][1][u][lane * VEC]);
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        float r = wtr[i] - row[i];
-                        acc[i] += r;
-                        sse = fmaf(r, r, sse);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) acc[i] += row[i];
+                for (int i = 0; i < VEC; ++i) {
+                    float r = wtr[i] - row[i];
+                    acc[i] += r;
+                    sse = fmaf(r, r, sse);
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += row[i];
             }
         }
         buf ^= 1;
@@ -670,7 +692,8 @@ static int launch_levels(const float* x, const Geom& g, const AccumPlan& pl, con
     if (pl.n_chunks > 0) {
         int64_t warps = pl.n_chunks * n_slices;
         unsigned blocks = (unsigned)ceil_div64(warps, ACC_WARPS);
-        constexpr size_t ring_bytes = (size_t)ACC_WARPS * 2 * 2 * L1_GROUP<VEC>::value * 32 * VEC * sizeof(float);
+        constexpr size_t ring_bytes = (size_t)ACC_WARPS * 2 * 2 * L1_GROUP<VEC>::value * 32 * VEC * sizeof(float) +
+                                      (size_t)ACC_WARPS * 2 * L1_GROUP<VEC>::value * sizeof(int4);
         static PerDeviceFlag attr_done;
         if (attr_done.pending()) {
             cudaError_t e = cudaFuncSetAttribute(seg_level1_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -47,6 +47,7 @@ struct Geom {
 int make_geom(Geom* g, const void* x, int64_t n_img, int C, int H, int W, int pH, int pW);
 
 __host__ __device__ __forceinline__ int64_t patch_base(const Geom& g, int64_t p) {
+    if (g.seq == 1) return p * g.img_stride;      // one patch per image (e.g. pre-flattened rows): no divisions
     int64_t n = p / g.seq;
     int s = (int)(p - n * g.seq);
     int ph = s / g.gW;

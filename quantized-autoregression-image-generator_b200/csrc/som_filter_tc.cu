@@ -57,6 +57,15 @@ static inline size_t smem_bytes(int tnf, int h) {
            2 * (size_t)(2 * (h + TAB_PAD) + 1) * sizeof(float) + 16;
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 template <int TNF>
 __device__ __forceinline__ void mma_tf32_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TNF >> 3) << 17) |
@@ -203,19 +212,25 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
             const uint32_t sw = (uint32_t)(ul & 7);
             int stage = 0;
             uint32_t phase = 0;
+            // explicit shared-space accesses through 32-bit addresses: written with pointers, the table reads and the tile
+            // stores compiled to GENERIC LD.E / ST.E.128 with 64-bit address arithmetic (ncu source page, round 2)
+            const uint32_t ring_u = smem_u32(ring), tab_hi_u = smem_u32(tab_hi), tab_lo_u = smem_u32(tab_lo);
             for (int kb = ksp; kb < nkb; kb += KS) {
                 mbar_wait_warp<false>(&bars.empty[stage], phase ^ 1, lane);
-                uint8_t* sa = ring + (size_t)stage * STAGE + row_off;
+                const uint32_t sa = ring_u + (uint32_t)stage * (uint32_t)STAGE + row_off;
                 // A[ul][jl] = w(jl - h - ul), jl = 32 kb + c: consecutive rows read consecutive table entries
-                const float* th = tab_hi + (kb * KBLK - P.h - ul + off);
-                const float* tl = tab_lo + (kb * KBLK - P.h - ul + off);
+                const uint32_t t_off = (uint32_t)(kb * KBLK - P.h - ul + off) * 4u;
+                const uint32_t th = tab_hi_u + t_off, tl = tab_lo_u + t_off;
 #pragma unroll
                 for (int qq = 0; qq < KBLK / 8; ++qq) {
                     const int q = qh + qq;
-                    const float4 hi = make_float4(th[4 * q], th[4 * q + 1], th[4 * q + 2], th[4 * q + 3]);
-                    const float4 lo = make_float4(tl[4 * q], tl[4 * q + 1], tl[4 * q + 2], tl[4 * q + 3]);
-                    *reinterpret_cast<float4*>(sa + ((((uint32_t)q) ^ sw) << 4)) = hi;
-                    *reinterpret_cast<float4*>(sa + A_BLK_BYTES + ((((uint32_t)q) ^ sw) << 4)) = lo;
+                    float4 hi, lo;
+                    hi.x = lds_f32(th + 16u * q); hi.y = lds_f32(th + 16u * q + 4u);
+                    hi.z = lds_f32(th + 16u * q + 8u); hi.w = lds_f32(th + 16u * q + 12u);
+                    lo.x = lds_f32(tl + 16u * q); lo.y = lds_f32(tl + 16u * q + 4u);
+                    lo.z = lds_f32(tl + 16u * q + 8u); lo.w = lds_f32(tl + 16u * q + 12u);
+                    sts_v4(sa + ((((uint32_t)q) ^ sw) << 4), hi);
+                    sts_v4(sa + (uint32_t)A_BLK_BYTES + ((((uint32_t)q) ^ sw) << 4), lo);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
