@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_l16_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
     pdl_launch_dependents();            // (the wait on the operand-split kernel comes after the barrier / TMEM prologue)
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET into the shared array: rounding the pointer through uintptr_t made the compiler
+    // forget the address space, and every access below compiled to generic LD.E / ST.E (cuobjdump, round 2)
+    uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int B_STAGE = B_BLK_BYTES / CG;       // this CTA's share of a 256-unit block
     constexpr int T_STAGE = TAIL_B_BYTES / CG;
     constexpr int M_STAGE = 2 * B_STAGE + T_STAGE;  // merged stage: [hi | lo | tail]

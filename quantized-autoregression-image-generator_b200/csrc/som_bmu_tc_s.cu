@@ -117,7 +117,9 @@ template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_s_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_t, const Params P) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET into the shared array: rounding the pointer through uintptr_t made the compiler
+    // forget the address space, and every access below compiled to generic LD.E / ST.E (cuobjdump, round 2)
+    uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_slots = tiles;
     uint8_t* a_tail = tiles + R * A_BLK_BYTES;
     uint8_t* ring = a_tail + TAIL_A_BYTES;

@@ -114,7 +114,9 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
     constexpr int STAGE = stage_bytes<TNF>();
     constexpr int B_BYTES = TNF * KBLK * 4;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET into the shared array: rounding the pointer through uintptr_t made the compiler
+    // forget the address space, and every access below compiled to generic LD.E / ST.E (cuobjdump, round 2)
+    uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     Barriers& bars = *reinterpret_cast<Barriers*>(ring + NSTAGE * STAGE);
     float* tab_hi = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(&bars) + sizeof(Barriers));
     const int off = P.h + TAB_PAD;
