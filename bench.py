@@ -375,9 +375,10 @@ def run_headline(args, dev, world, rank, peaks):
                 parts["slice: filter_W rows"] = _timed(lambda: ops.neighbourhood_filter(w[g0:g1], rng), reps)
                 parts["slice: multicast W~ rows + barrier"] = _timed(
                     lambda: ops.peer_bcast_rows(wth[lo_u - g0:hi_u - g0], mc["wt"] + lo_u * d * 4, max_own * d, rk, world, sig, 0), reps)
-            parts["slice: in-switch reduce of Rbar rows + halo"] = _timed(
-                lambda: ops.peer_reduce_rows(mc["packed"], tr._peer_packed, k, d, g0, g1, max_halo, rsum, tl, rk, world, sig, 1), reps)
-            parts["slice: filter_Rbar rows"] = _timed(lambda: ops.neighbourhood_filter(rsum, rng), reps)
+            scratch = torch.empty(max_halo, d, dtype=torch.float32, device=dev)
+            parts["slice: filter_Rbar rows, in-switch reduce of the rows + halo fused into its read"] = _timed(
+                lambda: ops.peer_reduce_filter_rows(mc["packed"], tr._peer_packed, k, d, g0, g1, max_halo, rng, scratch, gh,
+                                                    tl, rk, world, sig, 1), reps)
             # (Adam here re-broadcasts the CURRENT rows: lr = 0 keeps the replicas' weights unchanged)
             parts["slice: adam + multicast W rows + barrier"] = _timed(
                 lambda: ops.peer_adam_slice(w[lo_u:hi_u], mc["w"] + lo_u * d * 4, mm, vv, gh[lo_u - g0:hi_u - g0], max_own * d,

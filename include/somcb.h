@@ -249,6 +249,17 @@ SOM_API int som_peer_allreduce_f32(void* mc_buf, int64_t n, void* const* peer_bu
 SOM_API int som_peer_reduce_rows_f32(const void* mc_packed, void* const* peer_packed, int K, int D, int row0,
                              int row1, int max_rows, float* out_rows, float* out_tail, int rank, int world,
                              void* const* signal_pads, int channel, void* stream);
+/* The same reduction FUSED into its consumer: out_rows (row1 - row0 x D) = scale * T @ (sum over the ranks of rows
+ * [row0, row1)), T the neighbourhood matrix of a (row1 - row0)-unit codebook as in som_filter_ws_f32 (ws / ws_bytes:
+ * som_filter_workspace_bytes(row1 - row0, D, range)).  The filter's pre-pass reads the rows through the multicast
+ * address with the in-switch add, so no reduced copy exists in between; out_tail as above.  Shapes the tensor-core
+ * filter does not take run som_peer_reduce_rows_f32 into rows_scratch (max_rows x D floats) + som_filter_ws_f32.
+ * row0 < row1 (a rank that owns no rows calls som_peer_reduce_rows_f32 with row0 == row1).  Replaces, across ranks,
+ * loss.backward()'s S^T @ dL/dW~ (models/Codebook.py:128-130) after the ranks' accumulators exist.              */
+SOM_API int som_peer_reduce_filter_rows_f32(const void* mc_packed, void* const* peer_packed, int K, int D, int row0,
+                             int row1, int max_rows, double neighbourhood_range, float scale, float* rows_scratch,
+                             float* out_rows, float* out_tail, int rank, int world, void* const* signal_pads,
+                             int channel, void* ws, size_t ws_bytes, void* stream);
 /* n floats of local src_rows stored to mc_dst_rows on every rank, then a barrier over the ranks: when the call
  * has completed on a rank, every rank's rows have landed in its copy.  max_n = the largest n of any rank.      */
 SOM_API int som_peer_bcast_rows_f32(const float* src_rows, void* mc_dst_rows, int64_t n, int64_t max_n, int rank,

@@ -243,6 +243,8 @@ static inline float two_var_of(double neighbourhood_range) {
     return (float)(2.0 * variance);
 }
 
+float filter_two_var(double neighbourhood_range) { return two_var_of(neighbourhood_range); }
+
 }  // namespace som
 
 using namespace som;

@@ -23,6 +23,7 @@
 // Bound: tensor pipe / shared-memory operand bandwidth (A 4 KB + B TNF*32 B per MMA).
 // Algorithmic work: 2*K*D*(2h+1) flop; executed: 3 * 2*128*TNF*L per tile with L = 32*ceil((128+2h)/32).
 #include "som_common.cuh"
+#include "som_peer.cuh"
 #include "som_tc_ptx.cuh"
 
 namespace som {
@@ -81,17 +82,38 @@ __device__ __forceinline__ void mma_tf32_n(uint32_t tmem_d, uint64_t adesc, uint
 
 // Bt_hi / Bt_lo [D][Kp]: column h + j holds in[j][d] (hi / lo part), zero elsewhere.  32 x 32 tiles through shared
 // memory: reads coalesced along d, writes coalesced along j.
+// MC: `in` is the NVSwitch multicast address of the ranks' accumulator rows (som_peer.cu) and the load is the in-switch
+// reduction multimem.ld_reduce.add -- the reduce-scatter half of the data-parallel tail happens in this pre-pass's read,
+// with no reduced copy of the rows in between; block (0, 0) also reduces the packed buffer's 4-float tail exactly.
+struct PeerIn {
+    peer::Pads bufs;        // every rank's packed buffer (peer addresses), for the exact tail
+    int64_t q_tail;         // float4 index of the tail in a packed buffer
+    int world;
+    float4* tail_out;
+};
+
+template <bool MC>
 __global__ void __launch_bounds__(256) split_in_t_kernel(const float* __restrict__ in, int K, int D, int h, int Kp,
-                                                         float* __restrict__ Bhi, float* __restrict__ Blo) {
+                                                         float* __restrict__ Bhi, float* __restrict__ Blo, PeerIn pin) {
     pdl_begin();
     trace_stamp(s_trace_buf, 1);
     __shared__ float tile[32][33];
     const int jp0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    if (MC) {
+        const int rr = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;         // 32 rows x 8 quads (D % 4 == 0)
+        const int j = jp0 + rr - h, d = d0 + c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j >= 0 && j < K && d < D) v = peer::mm_ld_reduce(in + (int64_t)j * D + d);
+        tile[rr][c4] = v.x; tile[rr][c4 + 1] = v.y; tile[rr][c4 + 2] = v.z; tile[rr][c4 + 3] = v.w;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+            *pin.tail_out = peer::exact_tail(pin.bufs, pin.q_tail, pin.world);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int j = jp0 + ty + 8 * i - h, d = d0 + tx;
-        tile[ty + 8 * i][tx] = (j >= 0 && j < K && d < D) ? __ldg(in + (int64_t)j * D + d) : 0.f;
+        for (int i = 0; i < 4; ++i) {
+            const int j = jp0 + ty + 8 * i - h, d = d0 + tx;
+            tile[ty + 8 * i][tx] = (j >= 0 && j < K && d < D) ? __ldg(in + (int64_t)j * D + d) : 0.f;
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -356,8 +378,9 @@ size_t filter_tc_workspace_bytes(int K, int D, int h) {
     return pl.total;
 }
 
-int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, int h, float scale, void* ws,
-                     size_t ws_bytes, cudaStream_t st) {
+// pin != nullptr: `in` is a multicast address, read with the in-switch reduction (see split_in_t_kernel)
+int launch_filter_tc_in(const float* in, float* out, int K, int D, float two_var, int h, float scale, void* ws,
+                        size_t ws_bytes, cudaStream_t st, const ftc::PeerIn* pin) {
     using namespace ftc;
     Plan pl;
     make_plan(&pl, K, D, h);
@@ -368,7 +391,8 @@ int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, i
     float* Blo = (float*)((char*)ws + pl.off_lo);
     {
         dim3 grid((unsigned)(pl.Kp / 32), (unsigned)ceil_div64(D, 32));
-        launch_pdl(split_in_t_kernel, grid, 256, 0, st, in, K, D, h, pl.Kp, Bhi, Blo);
+        if (pin != nullptr) launch_pdl(split_in_t_kernel<true>, grid, 256, 0, st, in, K, D, h, pl.Kp, Bhi, Blo, *pin);
+        else launch_pdl(split_in_t_kernel<false>, grid, 256, 0, st, in, K, D, h, pl.Kp, Bhi, Blo, PeerIn{});
         int rc = check_launch("split_in_t_kernel");
         if (rc) return rc;
     }
@@ -401,6 +425,23 @@ int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, i
     if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
     launch_pdl(filter_reduce_kernel, blocks, 256, 0, st, P.partial, n, scale, out);
     return check_launch("filter_reduce_kernel");
+}
+
+int launch_filter_tc(const float* in, float* out, int K, int D, float two_var, int h, float scale, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+    return launch_filter_tc_in(in, out, K, D, two_var, h, scale, ws, ws_bytes, st, nullptr);
+}
+
+// som_peer.cu: out = scale * T @ (sum over the ranks of the rows at the multicast address mc_in), tail reduced exactly
+int launch_filter_tc_peer(const float* mc_in, float* out, int K, int D, float two_var, int h, float scale, void* ws,
+                          size_t ws_bytes, cudaStream_t st, const peer::Pads& bufs, int64_t q_tail, int world,
+                          float* tail_out) {
+    ftc::PeerIn pin;
+    pin.bufs = bufs;
+    pin.q_tail = q_tail;
+    pin.world = world;
+    pin.tail_out = reinterpret_cast<float4*>(tail_out);
+    return launch_filter_tc_in(mc_in, out, K, D, two_var, h, scale, ws, ws_bytes, st, &pin);
 }
 
 }  // namespace som

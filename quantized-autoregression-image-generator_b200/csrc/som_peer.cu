@@ -24,15 +24,14 @@
 // blocks: blocks x world NVLink atomics per kernel).  Spins are bounded (~4 s): a missing peer traps instead of hanging.
 // Buffers are caller-owned symmetric (peer-mapped + multicast) allocations; the library keeps no pointers.
 #include "som_common.cuh"
+#include "som_peer.cuh"
 
 namespace som {
 SOM_TRACE_TU(trace_set_peer)
 namespace peer {
 
-constexpr int MAX_WORLD = 16;
 constexpr int THREADS = 512;
 
-struct Pads { uint32_t* p[MAX_WORLD]; };       // flag area of every rank (peer-mapped addresses), layout at counter_of()
 
 __device__ __forceinline__ uint64_t gtimer() {
     uint64_t v;
@@ -96,36 +95,9 @@ __global__ void __launch_bounds__(32) barrier_kernel(Pads pads, int channel, int
     trace_stamp(s_trace_buf, 113);                               // every peer has arrived
 }
 
-__device__ __forceinline__ float4 mm_ld_reduce(const float* mc) {
-    float4 v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
-    return v;
-}
 __device__ __forceinline__ void mm_st(float* mc, const float4& v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
                  ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-// The 4-float tail [sse_hi, sse_lo, n / 4096, n % 4096] of the packed accumulator buffer is NOT reduced in the
-// switch: the in-switch fp32 adder is not exact enough for the loss (measured 1.2e-6 relative over 8 ranks), and the
-// patch count must be exact.  Every rank reads the R tails through the peer addresses and adds them in rank order,
-// the squared error in fp64 -- the same bits on every rank.
-__device__ __forceinline__ float4 exact_tail(const Pads& bufs, int64_t q_tail, int world) {
-    double sse = 0.0, cnt_hi = 0.0, cnt_lo = 0.0;
-    for (int r = 0; r < world; ++r) {
-        float4 t;
-        const float* p = reinterpret_cast<const float*>(bufs.p[r]) + 4 * q_tail;
-        asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p) : "memory");
-        sse += (double)t.x + (double)t.y;
-        cnt_hi += (double)t.z;
-        cnt_lo += (double)t.w;
-    }
-    const double cnt = cnt_hi * 4096.0 + cnt_lo;
-    const float hi = (float)sse;
-    const double c_hi = floor(cnt / 4096.0);
-    return make_float4(hi, (float)(sse - (double)hi), (float)c_hi, (float)(cnt - c_hi * 4096.0));
 }
 
 // in-place all-reduce of n4 float4 at the multicast address: rank r reduces and re-broadcasts quads [q0, q1);
@@ -256,6 +228,14 @@ static int grid_for(int64_t n4) {
 }
 
 }  // namespace peer
+
+// som_filter.cu / som_filter_tc.cu
+float filter_two_var(double neighbourhood_range);
+int filter_band_half_width(float two_var, int K);
+bool filter_tc_applicable(int K, int D, int h);
+int launch_filter_tc_peer(const float* mc_in, float* out, int K, int D, float two_var, int h, float scale, void* ws,
+                          size_t ws_bytes, cudaStream_t st, const peer::Pads& bufs, int64_t q_tail, int world,
+                          float* tail_out);
 }  // namespace som
 
 using namespace som;
@@ -313,6 +293,45 @@ extern "C" int som_peer_reduce_rows_f32(const void* mc_packed, void* const* peer
         (const float*)mc_packed, (int64_t)row0 * d4, (int64_t)row1 * d4, (int64_t)K * d4, (float4*)out_rows,
         (float4*)out_tail, bufs, world);
     return check_launch("peer_reduce_rows_kernel");
+}
+
+// Reduce-scatter fused into the consumer: G rows = scale * T @ (sum over the ranks of accumulator rows [row0, row1)), the
+// sum taken by the filter's own pre-pass as it reads (multimem.ld_reduce) -- no reduced copy of the rows, one kernel and
+// one pass over them less than som_peer_reduce_rows_f32 + som_filter_ws_f32.  Shapes the tensor-core filter does not
+// take fall back to exactly that pair (rows_scratch: max_rows x D floats).
+extern "C" int som_peer_reduce_filter_rows_f32(const void* mc_packed, void* const* peer_packed, int K, int D, int row0,
+                                               int row1, int max_rows, double neighbourhood_range, float scale,
+                                               float* rows_scratch, float* out_rows, float* out_tail, int rank,
+                                               int world, void* const* signal_pads, int channel, void* ws,
+                                               size_t ws_bytes, void* stream) {
+    SOM_REQUIRE(mc_packed && peer_packed && rows_scratch && out_rows && out_tail, SOM_E_BADARG,
+                "peer_reduce_filter_rows: null pointer");
+    SOM_REQUIRE(K > 0 && D > 0 && D % 4 == 0 && row0 >= 0 && row0 < row1 && row1 <= K && max_rows >= row1 - row0,
+                SOM_E_BADARG, "peer_reduce_filter_rows: K=%d D=%d rows [%d, %d) max %d (D must be a multiple of 4)", K,
+                D, row0, row1, max_rows);
+    SOM_REQUIRE(neighbourhood_range > 0.0, SOM_E_BADARG, "peer_reduce_filter_rows: neighbourhood_range=%g",
+                neighbourhood_range);
+    SOM_REQUIRE((((uintptr_t)mc_packed | (uintptr_t)rows_scratch | (uintptr_t)out_rows | (uintptr_t)out_tail) & 15) == 0,
+                SOM_E_BADARG, "peer_reduce_filter_rows: buffers must be 16-byte aligned");
+    SOM_REQUIRE(channel >= 0 && channel < 4, SOM_E_BADARG, "peer: channel=%d", channel);
+    const int rows = row1 - row0;
+    const float two_var = filter_two_var(neighbourhood_range);
+    const int h = filter_band_half_width(two_var, rows);
+    if (!(filter_tc_applicable(rows, D, h) && ws != nullptr)) {
+        int rc = som_peer_reduce_rows_f32(mc_packed, peer_packed, K, D, row0, row1, max_rows, rows_scratch, out_tail, rank,
+                                          world, signal_pads, channel, stream);
+        if (rc) return rc;
+        return som_filter_ws_f32(rows_scratch, out_rows, rows, D, neighbourhood_range, scale, ws, ws_bytes, stream);
+    }
+    Pads pads, bufs;
+    int rc = make_pads(&pads, signal_pads, rank, world);
+    if (rc) return rc;
+    rc = make_pads(&bufs, peer_packed, rank, world);
+    if (rc) return rc;
+    rc = launch_barrier(pads, channel, rank, world, (cudaStream_t)stream);      // every rank's accumulators are complete
+    if (rc) return rc;
+    return launch_filter_tc_peer((const float*)mc_packed + (int64_t)row0 * D, out_rows, rows, D, two_var, h, scale, ws,
+                                 ws_bytes, (cudaStream_t)stream, bufs, (int64_t)K * (D / 4), world, out_tail);
 }
 
 extern "C" int som_peer_bcast_rows_f32(const float* src_rows, void* mc_dst_rows, int64_t n, int64_t max_n, int rank,

@@ -56,6 +56,9 @@ SIGNATURES = {
     "som_peer_allreduce_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "som_peer_reduce_rows_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                          c_int, c_int, c_void_p, c_int, c_void_p]),
+    "som_peer_reduce_filter_rows_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_double, c_float,
+                                                c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
+                                                c_size_t, c_void_p]),
     "som_peer_bcast_rows_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int,
                                         c_void_p]),
     "som_peer_adam_slice_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,

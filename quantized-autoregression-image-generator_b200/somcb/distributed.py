@@ -183,13 +183,16 @@ class DataParallelSom(SomTrainer):
             bmu, x_acc, geom_acc = self._search(x, geom, w)
         ops.accumulate_packed(x_acc, geom_acc, bmu, wt, k, packed=self.packed)
         if sliced:
-            rsum = torch.empty(max(1, g1 - g0), d, dtype=torch.float32, device=w.device)
-            ops.peer_reduce_rows(self._mc["packed"], self._peer_packed, k, d, g0, g1, max_halo, rsum, self._tail_local,
-                                 rank, world, sig, 1)
+            rsum = torch.empty(max(1, max_halo), d, dtype=torch.float32, device=w.device)
             if hi > lo:
-                gh = ops.neighbourhood_filter(rsum[:g1 - g0], rng, scale=1.0)
+                # reduce-scatter fused into the filter's read: G rows = T @ (sum over ranks of Rbar rows [g0, g1))
+                gh = torch.empty(g1 - g0, d, dtype=torch.float32, device=w.device)
+                ops.peer_reduce_filter_rows(self._mc["packed"], self._peer_packed, k, d, g0, g1, max_halo, rng, rsum, gh,
+                                            self._tail_local, rank, world, sig, 1)
                 g_rows = gh[lo - g0:hi - g0]
             else:
+                ops.peer_reduce_rows(self._mc["packed"], self._peer_packed, k, d, g0, g1, max_halo, rsum,
+                                     self._tail_local, rank, world, sig, 1)
                 g_rows = self._tail_local[0:0]
             loss = ops.peer_adam_slice(w[lo:hi], self._mc["w"] + lo * d * 4, self.m.data[lo:hi], self.v.data[lo:hi],
                                        g_rows, max_own * d, d, self.lr, self.t_dev, self._tail_local, rank, world,

@@ -390,6 +390,28 @@ def peer_reduce_rows(mc_packed, peer_ptrs, num_units, dim, row0, row1, max_rows,
                                            int(channel), _stream(out_rows)))
 
 
+def peer_reduce_filter_rows(mc_packed, peer_ptrs, num_units, dim, row0, row1, max_rows, neighbourhood_range, rows_scratch,
+                            out_rows, out_tail, rank, world, signal_ptrs, channel, scale=1.0):
+    """Reduce-scatter fused into the filter: out_rows = scale * T @ (sum over ranks of accumulator rows [row0, row1))."""
+    lib = _lib.load()
+    rows = int(row1) - int(row0)
+    rows_scratch = _req(rows_scratch, torch.float32, "rows_scratch")
+    out_rows = _req(out_rows, torch.float32, "out_rows")
+    out_tail = _req(out_tail, torch.float32, "out_tail")
+    if rows_scratch.numel() < int(max_rows) * int(dim) or out_rows.numel() < rows * int(dim):
+        raise ValueError("rows_scratch must hold max_rows x D floats and out_rows (row1 - row0) x D")
+    with torch.cuda.device(out_rows.device):
+        ws, ws_bytes = _workspace(lib.som_filter_workspace_bytes(rows, int(dim), float(neighbourhood_range)),
+                                  out_rows.device)
+        check("som_peer_reduce_filter_rows_f32",
+              lib.som_peer_reduce_filter_rows_f32(int(mc_packed), _pads(peer_ptrs), int(num_units), int(dim), int(row0),
+                                                  int(row1), int(max_rows), float(neighbourhood_range), float(scale),
+                                                  _ptr(rows_scratch), _ptr(out_rows), _ptr(out_tail), int(rank),
+                                                  int(world), _pads(signal_ptrs), int(channel), _ptr(ws), ws_bytes,
+                                                  _stream(out_rows)))
+    return out_rows
+
+
 def peer_bcast_rows(src_rows, mc_dst, max_n, rank, world, signal_ptrs, channel):
     lib = _lib.load()
     src_rows = _req(src_rows, torch.float32, "src_rows")

@@ -92,6 +92,42 @@ def main():
                   f"identical on every rank: {same}")
         ok &= err <= 1e-6 and same
 
+        # ---- reduce-scatter fused into the filter's read against reduce_rows + filter and the fp64 sum -------------
+        kk, dd, rng_f = 4096, 64, 2048
+        packed, mc_p, peers_p = pm.alloc(kk * dd + 4)
+        g = torch.Generator(device=dev).manual_seed(40 + rank)
+        packed[:kk * dd].copy_(torch.randn(kk * dd, generator=g, device=dev))
+        packed[kk * dd:].copy_(torch.tensor([1.5 + rank, 0.25, 0.0, 100.0 + rank], device=dev))
+        allp = [torch.empty(kk * dd + 4, device=dev) for _ in range(world)]
+        dist.all_gather(allp, packed)
+        total = torch.stack([a[:kk * dd] for a in allp]).double().sum(dim=0).view(kk, dd)
+        lo_u, hi_u = somcb.shard_bounds(kk, world, rank)
+        hw = ops.filter_half_width(kk, rng_f)
+        g0, g1 = max(0, lo_u - hw), min(kk, hi_u + hw)
+        max_rows = kk
+        scratch = torch.empty(max_rows, dd, device=dev)
+        fused = torch.empty(g1 - g0, dd, device=dev)
+        tail_a, tail_b = torch.empty(4, device=dev), torch.empty(4, device=dev)
+        rows = torch.empty(g1 - g0, dd, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ops.peer_reduce_filter_rows(mc_p, peers_p, kk, dd, g0, g1, max_rows, rng_f, scratch, fused, tail_a, pm.rank,
+                                    pm.world, pm.signal_ptrs, 3)
+        ops.peer_reduce_rows(mc_p, peers_p, kk, dd, g0, g1, max_rows, rows, tail_b, pm.rank, pm.world, pm.signal_ptrs, 3)
+        two_step = ops.neighbourhood_filter(rows, rng_f)
+        want_f = ops.neighbourhood_filter(total[g0:g1].float().contiguous(), rng_f).double()
+        torch.cuda.synchronize()
+        same_f = bool(torch.equal(fused, two_step)) and bool(torch.equal(tail_a, tail_b))
+        err_f = float((fused.double() - want_f).norm() / want_f.norm())
+        want_tail = sum(1.75 + r for r in range(world))
+        tail_ok = abs(float(tail_a[0]) + float(tail_a[1]) - want_tail) <= 1e-6 * want_tail and \
+            float(tail_a[2]) * 4096 + float(tail_a[3]) == sum(100.0 + r for r in range(world))
+        if rank == 0:
+            print(f"[peer] filter with the in-switch reduce fused into its read: identical to reduce_rows + filter "
+                  f"{same_f}, rel error vs the fp64 sum {err_f:.2e}, exact tail {tail_ok}")
+        ok &= same_f and err_f <= 1e-6 and tail_ok
+        dist.barrier()
+
     # ---- unit-sharded search + histogram ---------------------------------------------------------
     pd, k = (8, 8), 8192
     w = trained_like_codebook(k, pd, 3).to(dev)
