@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, 1) step_small_kernel(const Params P) 
             if (i < RB && g * RB + i < R) P.Wt[(int64_t)(a0 + g * RB + i) * D + d] = rows[i];
     }
     stamp(1);
-    grid.sync();
+    // (no grid barrier here: the search below reads W and x only; W~ is first needed in phase 2)
     stamp(2);
 
     // ---- phase 1: scores of (a block of patches) x (a chunk of 64 units): candidates per (chunk, patch) --------------
