@@ -2,11 +2,11 @@
 //
 // The whole iteration of /root/reference/train_codebook.py:225-249 -- forward with the Gaussian neighbourhood
 // (models/Codebook.py:102-135), mse_loss, backward, Adam -- in the factorised form of SURVEY.md A.3, as ONE cooperative
-// kernel with three grid-wide barriers instead of ~13 launches: at this size a launch (~4 us even from a CUDA graph) costs
+// kernel with two grid-wide barriers instead of ~13 launches: at this size a launch (~4 us even from a CUDA graph) costs
 // more than any of the kernels.  One CTA per SM; CTA b owns the contiguous unit rows [b R, (b+1) R):
 //
 //   phase 0  W~ rows of the own units = sum_t w(t) W[a+t]            (band filter, input rows streamed once per CTA)
-//   ---- grid barrier ----
+//   (no barrier: the search reads W, not W~)
 //   phase 1  BMU of the own patches (n / CTAs each) against ALL units (fp32 FFMA, unit tiles staged in shared memory,
 //            score x.c - ||c||^2 / 2, lowest index on ties)
 //   ---- grid barrier ----
