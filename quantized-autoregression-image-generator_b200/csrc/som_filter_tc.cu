@@ -32,7 +32,10 @@ namespace ftc {
 using namespace tc;
 
 constexpr int TMU = 128;                     // units per tile (UMMA M)
-constexpr int NSTAGE = 3;
+constexpr int CK = 5;                        // k-blocks that share one Toeplitz strip of the A operand
+constexpr int STRIP_ROWS = TMU + KBLK * (CK - 1);        // 256: one builder thread per row
+constexpr int STRIP_BYTES = STRIP_ROWS * KBLK * 4;       // 32 KB (hi or lo)
+template <int TNF> constexpr int nstage_b() { return TNF == 128 ? 2 : 4; }      // B ring: 64 KB either way
 constexpr int NACC = 4;                      // TMEM accumulators, k-block kb goes to kb % NACC (see the MMA loop)
 constexpr int BUILD_WARPS = 8;                // two threads per unit row, 16 inner positions each
 constexpr int NUM_THREADS = (2 + BUILD_WARPS) * 32;      // 320
@@ -43,18 +46,18 @@ struct Params {
     int K, D, h, nkb;
     float two_var, scale;
     float* out;
-    int ks;                 // k-split: CTA blockIdx.z takes the k-blocks kb = z (mod ks); ks is 1 or NACC
+    int q, na;              // accumulation chains: chain a = k-blocks [a q, (a + 1) q), na <= NACC of them
+    int ks;                 // k-split: CTA blockIdx.z runs chain z; ks is 1 or na
     float* partial;         // ks > 1: [ks][K][D] unscaled partial sums, added by filter_reduce_kernel
 };
 
 struct __align__(8) Barriers {
-    uint64_t full[NSTAGE], empty[NSTAGE], acc_full;
+    uint64_t b_full[4], b_empty[4], s_full[2], s_empty[2], acc_full;
     uint32_t tmem_base, pad;
 };
 
-template <int TNF> constexpr int stage_bytes() { return 2 * A_BLK_BYTES + 2 * TNF * KBLK * 4; }
 static inline size_t smem_bytes(int tnf, int h) {
-    return 1024 + (size_t)NSTAGE * (2 * A_BLK_BYTES + 2 * tnf * KBLK * 4) + sizeof(Barriers) +
+    return 1024 + 4 * (size_t)STRIP_BYTES + (size_t)(tnf == 128 ? 2 : 4) * (2 * tnf * KBLK * 4) + sizeof(Barriers) +
            2 * (size_t)(2 * (h + TAB_PAD) + 1) * sizeof(float) + 16;
 }
 
@@ -65,6 +68,10 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_v4(uint32_t addr, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
 
 template <int TNF>
@@ -133,13 +140,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                  const Params P) {
     pdl_launch_dependents();            // (the wait comes after the barrier / weight-table / TMEM prologue)
-    constexpr int STAGE = stage_bytes<TNF>();
+    // TNF = 64 (D <= 64): a stage's B_hi and B_lo blocks are adjacent 64-row K-major tiles, i.e. ONE 128-row tile
+    // [B_hi ; B_lo].  An M128 x N64 tf32 MMA occupies the tensor pipe as long as an N128 one (71 against 67 cycles,
+    // profiles/r01_mma_issue_microbench.log), so A_hi and A_lo are each multiplied with the concatenated tile: two N128
+    // MMAs per k-step instead of three N64 ones (134 against 214 cycles).  Columns [0, 64) of the accumulator collect
+    // A.B_hi, columns [64, 128) A.B_lo (now including the lo.lo term); the epilogue adds the halves.
+    constexpr bool CAT = (TNF == 64);
+    constexpr int ACC_COLS = CAT ? 2 * TNF : TNF;
+    constexpr int NSB = nstage_b<TNF>();
     constexpr int B_BYTES = TNF * KBLK * 4;
+    constexpr int B_STAGE = 2 * B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment as an OFFSET into the shared array: rounding the pointer through uintptr_t made the compiler
     // forget the address space, and every access below compiled to generic LD.E / ST.E (cuobjdump, round 2)
-    uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    Barriers& bars = *reinterpret_cast<Barriers*>(ring + NSTAGE * STAGE);
+    uint8_t* strips = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_ring = strips + 4 * STRIP_BYTES;          // [strip 0: hi | lo][strip 1: hi | lo][B stages]
+    Barriers& bars = *reinterpret_cast<Barriers*>(b_ring + NSB * B_STAGE);
     float* tab_hi = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(&bars) + sizeof(Barriers));
     const int off = P.h + TAB_PAD;
     const int tab_n = 2 * off + 1;
@@ -148,13 +164,17 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ut = blockIdx.x, ct = blockIdx.y;
-    // k-split (few tiles, e.g. a data-parallel rank's slice of units): the NACC round-robin accumulators of the unsplit
-    // kernel become NACC CTAs -- CTA z runs exactly the accumulation chain of accumulator z, and filter_reduce_kernel
-    // adds the partial tiles in the same fixed order, so the result is bit-identical to the unsplit kernel's
+    // k-split (few tiles, e.g. a data-parallel rank's slice of units): the accumulation chains of the unsplit kernel
+    // (chain a = k-blocks [a q, (a + 1) q), one TMEM accumulator each) become CTAs -- CTA z runs exactly chain z, and
+    // filter_reduce_kernel adds the partial tiles in the same fixed order, so the result is bit-identical to the
+    // unsplit kernel's
     const int ksp = (int)blockIdx.z, KS = P.ks;
+    const int kb_lo = KS > 1 ? ksp * P.q : 0;
+    const int kb_hi = KS > 1 ? (kb_lo + P.q < P.nkb ? kb_lo + P.q : P.nkb) : P.nkb;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.full[s], 1 + BUILD_WARPS); mbar_init(&bars.empty[s], 1); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(&bars.b_full[s], 1); mbar_init(&bars.b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.s_full[s], BUILD_WARPS); mbar_init(&bars.s_empty[s], 1); }
         mbar_init(&bars.acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -173,14 +193,13 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
-                     "r"(NACC * TNF));
+                     "r"(NACC * ACC_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
-    const int nkb = P.nkb;
     pdl_wait();
     trace_stamp(s_trace_buf, 2);
 
@@ -189,85 +208,114 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = ksp; kb < nkb; kb += KS) {
-                mbar_wait(&bars.empty[stage], phase ^ 1);
-                uint8_t* sb = ring + (size_t)stage * STAGE + 2 * A_BLK_BYTES;
-                mbar_expect_tx(&bars.full[stage], 2 * B_BYTES);
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                mbar_wait(&bars.b_empty[stage], phase ^ 1);
+                uint8_t* sb = b_ring + (size_t)stage * B_STAGE;
+                mbar_expect_tx(&bars.b_full[stage], 2 * B_BYTES);
                 // padded inner coordinate of unit tile ut starts at ut * 128 (= a0 - h + h)
-                tma_load_2d(&map_bhi, &bars.full[stage], sb, ut * TMU + kb * KBLK, ct * TNF);
-                tma_load_2d(&map_blo, &bars.full[stage], sb + B_BYTES, ut * TMU + kb * KBLK, ct * TNF);
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                tma_load_2d(&map_bhi, &bars.b_full[stage], sb, ut * TMU + kb * KBLK, ct * TNF);
+                tma_load_2d(&map_blo, &bars.b_full[stage], sb + B_BYTES, ut * TMU + kb * KBLK, ct * TNF);
+                if (++stage == NSB) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
+        // The issuing thread paces this kernel (round-2 counters: 8 MMAs cost ~150 cycles of issue per k-block, the
+        // scalar code around them ~540: descriptors rebuilt from pointers, an integer division for the chain, clock
+        // reads), so everything per k-block is an increment: descriptors are base + offset in the 16-byte address field
+        // (shared addresses < 256 KB fit its 14 bits), the chain index is a counter.
         const bool leader = elect_one();
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int kb = ksp; kb < nkb; kb += KS) {
-            mbar_wait(&bars.full[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(ring + (size_t)stage * STAGE);
-            const uint64_t ahi = umma_desc(sa), alo = umma_desc(sa + A_BLK_BYTES);
-            const uint64_t bhi = umma_desc(sa + 2 * A_BLK_BYTES), blo = umma_desc(sa + 2 * A_BLK_BYTES + B_BYTES);
-            // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of
-            // the accumulation chain (measured 1.7e-6 relative after 372 MMAs into one accumulator, band 851): the
-            // k-blocks are dealt round-robin to NACC accumulators and the epilogue adds those in fp32 (4e-7).
-            const uint32_t d_addr = tmem_base + (KS > 1 ? 0u : (uint32_t)(kb % NACC) * TNF);
-            if (leader) {
+        const uint32_t strip0 = smem_u32(strips), bring0 = smem_u32(b_ring);
+        const uint64_t a_desc0 = umma_desc(strip0), b_desc0 = umma_desc(bring0);
+        const uint32_t bempty0 = smem_u32(&bars.b_empty[0]), sempty0 = smem_u32(&bars.s_empty[0]);
+        const uint32_t accfull = smem_u32(&bars.acc_full);
+        int stage = 0, sbuf = 0;
+        uint32_t phase = 0, sphase = 0;
+        int in_chain = 0;                                     // k-blocks already issued into the current chain (KS == 1)
+        uint32_t d_addr = tmem_base;
+        bool first = true;
+        for (int c0 = kb_lo; c0 < kb_hi; c0 += CK) {
+            const int c1 = c0 + CK < kb_hi ? c0 + CK : kb_hi;
+            mbar_wait(&bars.s_full[sbuf], sphase);
+            uint64_t a_desc = a_desc0 + (uint64_t)((uint32_t)sbuf * (uint32_t)(2 * STRIP_BYTES >> 4));
+            for (int kb = c0; kb < c1; ++kb) {
+                mbar_wait(&bars.b_full[stage], phase);
+                tc_fence_after();
+                // k-block c0 + j of the strip = its rows [32 j, 32 j + 128): 4 KB further on, still 1024-byte aligned
+                const uint64_t ahi = a_desc, alo = a_desc + (uint64_t)(STRIP_BYTES >> 4);
+                const uint64_t bhi = b_desc0 + (uint64_t)((uint32_t)stage * (uint32_t)(B_STAGE >> 4));
+                const uint64_t blo = bhi + (uint64_t)(B_BYTES >> 4);
+                // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of
+                // the accumulation chain (measured 1.7e-6 relative after 372 MMAs into one accumulator, band 851): the
+                // k-blocks are dealt to NACC chains with an accumulator each and the epilogue adds those in fp32 (4e-7).
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < KBLK / 8; ++ks) {
-                    mma_tf32_n<TNF>(d_addr, ahi + 2u * ks, bhi + 2u * ks, (kb >= NACC || ks != 0) ? 1u : 0u);
-                    mma_tf32_n<TNF>(d_addr, alo + 2u * ks, bhi + 2u * ks, 1u);
-                    mma_tf32_n<TNF>(d_addr, ahi + 2u * ks, blo + 2u * ks, 1u);
+                    for (int ks = 0; ks < KBLK / 8; ++ks) {
+                        const uint32_t acc0 = (!first || ks != 0) ? 1u : 0u;
+                        if (CAT) {
+                            mma_tf32_n<ACC_COLS>(d_addr, ahi + 2u * ks, bhi + 2u * ks, acc0);
+                            mma_tf32_n<ACC_COLS>(d_addr, alo + 2u * ks, bhi + 2u * ks, 1u);
+                        } else {
+                            mma_tf32_n<TNF>(d_addr, ahi + 2u * ks, bhi + 2u * ks, acc0);
+                            mma_tf32_n<TNF>(d_addr, alo + 2u * ks, bhi + 2u * ks, 1u);
+                            mma_tf32_n<TNF>(d_addr, ahi + 2u * ks, blo + 2u * ks, 1u);
+                        }
+                    }
+                    tc_commit_addr(bempty0 + 8u * (uint32_t)stage);
+                    if (kb + 1 == c1) tc_commit_addr(sempty0 + 8u * (uint32_t)sbuf);
+                    if (kb + 1 == kb_hi) tc_commit_addr(accfull);
                 }
-                tc_commit(&bars.empty[stage]);
-                if (kb + KS >= nkb) tc_commit(&bars.acc_full);
+                first = false;
+                if (KS == 1 && ++in_chain == P.q) { in_chain = 0; d_addr += ACC_COLS; first = true; }
+                a_desc += (uint64_t)((KBLK * 128) >> 4);
+                if (++stage == NSB) { stage = 0; phase ^= 1; }
             }
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            if (++sbuf == 2) { sbuf = 0; sphase ^= 1; }
         }
     } else {
         // ================================ A builders, then epilogue =====================
         {
-            const int bt = threadIdx.x - 64;
-            const int ul = bt & (TMU - 1);                      // unit row of the tile this thread builds
-            const int qh = (bt >> 7) * (KBLK / 8);              // its half of the row's eight 16-byte chunks
-            const uint32_t row_off = (uint32_t)ul * 128u;
-            const uint32_t sw = (uint32_t)(ul & 7);
-            int stage = 0;
-            uint32_t phase = 0;
-            // explicit shared-space accesses through 32-bit addresses: written with pointers, the table reads and the tile
-            // stores compiled to GENERIC LD.E / ST.E.128 with 64-bit address arithmetic (ncu source page, round 2)
-            const uint32_t ring_u = smem_u32(ring), tab_hi_u = smem_u32(tab_hi), tab_lo_u = smem_u32(tab_lo);
-            for (int kb = ksp; kb < nkb; kb += KS) {
-                mbar_wait_warp<false>(&bars.empty[stage], phase ^ 1, lane);
-                const uint32_t sa = ring_u + (uint32_t)stage * (uint32_t)STAGE + row_off;
-                // A[ul][jl] = w(jl - h - ul), jl = 32 kb + c: consecutive rows read consecutive table entries
-                const uint32_t t_off = (uint32_t)(kb * KBLK - P.h - ul + off) * 4u;
-                const uint32_t th = tab_hi_u + t_off, tl = tab_lo_u + t_off;
+            // The A operand of CK consecutive k-blocks is ONE Toeplitz strip: with the tile's unit rows in reverse order
+            // (MMA row m = unit 127 - m) the block of k-block c0 + j is rows [32 j, 32 j + 128) of
+            //     S[r][c] = w(32 c0 + r + c - h - 127),   r < 128 + 32 (CK - 1),
+            // so the builders write 256 rows per CK = 5 k-blocks instead of 128 per k-block (2.5x fewer shared stores).
+            // One thread per strip row, all eight 16-byte chunks of it.
+            const int r = threadIdx.x - 64;                    // strip row of this thread
+            const uint32_t row_off = (uint32_t)r * 128u;
+            const uint32_t sw = (uint32_t)(r & 7);
+            const uint32_t strips_u = smem_u32(strips), tab_hi_u = smem_u32(tab_hi), tab_lo_u = smem_u32(tab_lo);
+            int sbuf = 0;
+            uint32_t sphase = 0;
+            for (int c0 = kb_lo; c0 < kb_hi; c0 += CK) {
+                const int nk = c0 + CK < kb_hi ? CK : kb_hi - c0;
+                mbar_wait_warp<false>(&bars.s_empty[sbuf], sphase ^ 1, lane);
+                if (r < TMU + KBLK * (nk - 1)) {
+                    const uint32_t sa = strips_u + (uint32_t)sbuf * (uint32_t)(2 * STRIP_BYTES) + row_off;
+                    const uint32_t t_off = (uint32_t)(c0 * KBLK + r - P.h - (TMU - 1) + off) * 4u;
+                    const uint32_t th = tab_hi_u + t_off, tl = tab_lo_u + t_off;
 #pragma unroll
-                for (int qq = 0; qq < KBLK / 8; ++qq) {
-                    const int q = qh + qq;
-                    float4 hi, lo;
-                    hi.x = lds_f32(th + 16u * q); hi.y = lds_f32(th + 16u * q + 4u);
-                    hi.z = lds_f32(th + 16u * q + 8u); hi.w = lds_f32(th + 16u * q + 12u);
-                    lo.x = lds_f32(tl + 16u * q); lo.y = lds_f32(tl + 16u * q + 4u);
-                    lo.z = lds_f32(tl + 16u * q + 8u); lo.w = lds_f32(tl + 16u * q + 12u);
-                    sts_v4(sa + ((((uint32_t)q) ^ sw) << 4), hi);
-                    sts_v4(sa + (uint32_t)A_BLK_BYTES + ((((uint32_t)q) ^ sw) << 4), lo);
+                    for (int q = 0; q < KBLK / 4; ++q) {
+                        float4 hi, lo;
+                        hi.x = lds_f32(th + 16u * q); hi.y = lds_f32(th + 16u * q + 4u);
+                        hi.z = lds_f32(th + 16u * q + 8u); hi.w = lds_f32(th + 16u * q + 12u);
+                        lo.x = lds_f32(tl + 16u * q); lo.y = lds_f32(tl + 16u * q + 4u);
+                        lo.z = lds_f32(tl + 16u * q + 8u); lo.w = lds_f32(tl + 16u * q + 12u);
+                        sts_v4(sa + ((((uint32_t)q) ^ sw) << 4), hi);
+                        sts_v4(sa + (uint32_t)STRIP_BYTES + ((((uint32_t)q) ^ sw) << 4), lo);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.full[stage]);
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                if (lane == 0) mbar_arrive(&bars.s_full[sbuf]);
+                if (++sbuf == 2) { sbuf = 0; sphase ^= 1; }
             }
         }
         if (warp >= 6) goto done;                               // warps 2-5 own the four TMEM lane quarters
-        // epilogue: TMEM lane quarter (warp & 3), 32 columns at a time
+        // epilogue: TMEM lane quarter (warp & 3), 32 columns at a time; lane m of the accumulator is unit 127 - m
         mbar_wait_warp<true>(&bars.acc_full, 0, lane);
         tc_fence_after();
         const int lg = warp & 3;
-        const int u = ut * TMU + lg * 32 + lane;
+        const int u = ut * TMU + (TMU - 1) - (lg * 32 + lane);
         const bool row_ok = u < P.K;
         const bool v4 = ((P.D & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
         float* orow = (KS > 1 ? P.partial + (int64_t)ksp * P.K * P.D : P.out) + (int64_t)(row_ok ? u : 0) * P.D;
@@ -278,11 +326,24 @@ filter_tc_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_const
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32);
             tmem_ld32_issue(taddr, v);
             tmem_ld_wait(v);
-            if (KS == 1) {
+            if (CAT) {                                           // chain value = (A.B_hi columns) + (A.B_lo columns)
+                tmem_ld32_issue(taddr + (uint32_t)TNF, w);
+                tmem_ld_wait(w);
 #pragma unroll
-                for (int a = 1; a < NACC; ++a) {                 // fixed order: ((a0 + a1) + a2) + a3
-                    tmem_ld32_issue(taddr + (uint32_t)(a * TNF), w);
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+            }
+            if (KS == 1) {
+#pragma unroll 1
+                for (int a = 1; a < P.na; ++a) {                 // fixed order: ((a0 + a1) + a2) + a3
+                    tmem_ld32_issue(taddr + (uint32_t)(a * ACC_COLS), w);
                     tmem_ld_wait(w);
+                    if (CAT) {
+                        uint32_t w2[32];
+                        tmem_ld32_issue(taddr + (uint32_t)(a * ACC_COLS + TNF), w2);
+                        tmem_ld_wait(w2);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) + __uint_as_float(w2[i]));
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
                 }
@@ -309,26 +370,25 @@ done:
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NACC * TNF));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NACC * ACC_COLS));
     }
 }
 
 // out = scale * (((p0 + p1) + p2) + p3): the unsplit epilogue's order
-__global__ void __launch_bounds__(256) filter_reduce_kernel(const float* __restrict__ partial, int64_t n, float scale,
-                                                            float* __restrict__ out) {
+__global__ void __launch_bounds__(256) filter_reduce_kernel(const float* __restrict__ partial, int64_t n, int na,
+                                                            float scale, float* __restrict__ out) {
     pdl_begin();
     trace_stamp(s_trace_buf, 3);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         float v = partial[i];
-#pragma unroll
-        for (int a = 1; a < NACC; ++a) v += partial[(int64_t)a * n + i];
+        for (int a = 1; a < na; ++a) v += partial[(int64_t)a * n + i];
         out[i] = scale * v;
     }
 }
 
 struct Plan {
-    int h, L, nkb, Kp, tnf, ks;
+    int h, L, nkb, Kp, tnf, ks, q, na;
     size_t off_hi, off_lo, off_part, total;
 };
 
@@ -344,7 +404,9 @@ static void make_plan(Plan* pl, int K, int D, int h) {
     pl->off_lo = one;
     // static rule: with fewer tiles than half the SMs, the NACC accumulation chains of a tile go to NACC CTAs
     const int64_t tiles = (int64_t)n_ut * ((D + pl->tnf - 1) / pl->tnf);
-    pl->ks = (tiles * 2 <= sm_count()) ? NACC : 1;
+    pl->q = (pl->nkb + NACC - 1) / NACC;
+    pl->na = (pl->nkb + pl->q - 1) / pl->q;
+    pl->ks = (tiles * 2 <= sm_count()) ? pl->na : 1;
     pl->off_part = 2 * one;
     pl->total = 2 * one + (pl->ks > 1 ? align_up((size_t)pl->ks * K * D * sizeof(float), 1024) : 0);
 }
@@ -405,6 +467,7 @@ int launch_filter_tc_in(const float* in, float* out, int K, int D, float two_var
     if (rc) return rc;
     Params P;
     P.K = K; P.D = D; P.h = h; P.nkb = pl.nkb; P.two_var = two_var; P.scale = scale; P.out = out;
+    P.q = pl.q; P.na = pl.na;
     P.ks = pl.ks; P.partial = (float*)((char*)ws + pl.off_part);
     const size_t smem = smem_bytes(pl.tnf, h);
     static PerDeviceFlag attr_done;
@@ -423,7 +486,7 @@ int launch_filter_tc_in(const float* in, float* out, int K, int D, float two_var
     const int64_t n = (int64_t)K * D;
     int blocks = (int)ceil_div64(n, 256 * 4);
     if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-    launch_pdl(filter_reduce_kernel, blocks, 256, 0, st, P.partial, n, scale, out);
+    launch_pdl(filter_reduce_kernel, blocks, 256, 0, st, P.partial, n, pl.ks, scale, out);
     return check_launch("filter_reduce_kernel");
 }
 
