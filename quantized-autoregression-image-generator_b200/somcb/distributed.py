@@ -175,12 +175,13 @@ class DataParallelSom(SomTrainer):
             else:
                 src = self._tail_local[0:0]                  # no rows of its own: takes part in the barrier only
             ops.peer_bcast_rows(src, self._mc["wt"] + lo * d * 4, max_own * d, rank, world, sig, 0)
-            wt = self._wt
+            wt, side = self._wt, None
         else:
-            wt = ops.neighbourhood_filter(w, rng)
+            wt, side = self._fork_filter(w, rng)             # beside norms / operand split / the start of the search
         x_acc, geom_acc = x, geom
         if bmu is None:
             bmu, x_acc, geom_acc = self._search(x, geom, w)
+        self._join_filter(side)
         ops.accumulate_packed(x_acc, geom_acc, bmu, wt, k, packed=self.packed)
         if sliced:
             rsum = torch.empty(max(1, max_halo), d, dtype=torch.float32, device=w.device)

@@ -27,7 +27,7 @@ class SomTrainer:
 
     def __init__(self, codebook, lr, neighbourhood_step, lr_step=100000, global_steps=0,
                  betas=(0.5, 0.999), eps=1e-8, ops=None, reduce_fn=None, world_size=1,
-                 use_cuda_graph=False, check_nan=False, small_step_kernel=True):
+                 use_cuda_graph=False, check_nan=False, small_step_kernel=True, overlap_filter=True):
         """``codebook``: a somcb.Codebook on a CUDA device.  ``reduce_fn(packed)`` sums the packed
         accumulator buffer in place across data-parallel ranks (None: single device).
 
@@ -40,7 +40,13 @@ class SomTrainer:
         (one-time kernel attribute set-up and NCCL communicator creation must not happen during capture).
 
         ``check_nan``: the reference's ``NaN encountered during training`` guard (train_codebook.py:237-238);
-        it reads the loss back, i.e. one host synchronisation per step, so it is off by default."""
+        it reads the loss back, i.e. one host synchronisation per step, so it is off by default.
+
+        ``overlap_filter``: W~ = T @ W is only needed by the accumulation, the search reads W -- so the filter runs on
+        a side stream beside norms, operand split and the start of the search (fork / join with stream waits, also
+        inside a captured graph) instead of in front of them.  Measured on B200 (graph-replayed C4 step, one GPU,
+        alternating A/B inside one process, tools/overlap_ab.py): 1.282 -> 1.259 ms at 262 144 patches, -7.7 us at
+        131 072 (an N = 8 rank's share), equal within the run-to-run noise at 1 048 576.  False keeps one stream."""
         self.cb = codebook
         self.lr = float(lr)
         self.neighbourhood_step = int(neighbourhood_step)
@@ -53,6 +59,9 @@ class SomTrainer:
         self.world_size = int(world_size)
         self.check_nan = bool(check_nan)
         self.small_step_kernel = bool(small_step_kernel)    # False: always the separate kernels (tests, A/B)
+        self.overlap_filter = bool(overlap_filter)
+        self._side = None                                   # side stream of the W~ filter
+        self._wt_side = None                                # its output (kept: written on one stream, read on another)
         w = codebook.codebook.weight
         # the reference does not checkpoint Adam state: a resume restarts the moments at zero
         self.m = torch.zeros_like(w, requires_grad=False)
@@ -141,10 +150,11 @@ class SomTrainer:
                                                  betas=self.betas, eps=self.eps)
             return loss
 
-        wt = ops.neighbourhood_filter(w, rng)
+        wt, side = self._fork_filter(w, rng)
         x_acc, geom_acc = x, geom
         if bmu is None:
             bmu, x_acc, geom_acc = self._search(x, geom, w)
+        self._join_filter(side)
         packed = self.packed
         ops.accumulate_packed(x_acc, geom_acc, bmu, wt, k, packed=packed)
         if self.reduce_fn is not None:
@@ -155,6 +165,28 @@ class SomTrainer:
                                 eps=self.eps)
         self.last_bmu = bmu
         return loss
+
+    def _fork_filter(self, w, rng):
+        """W~ = T @ W (models/Codebook.py:112-130 forward).  The search that follows does not read it, so on a CUDA
+        device it is enqueued on a side stream that forks from the current one; ``_join_filter`` makes the current
+        stream wait for it before the accumulation.  Returns (W~, side stream or None)."""
+        ops = self.ops
+        if not (self.overlap_filter and w.is_cuda):
+            return ops.neighbourhood_filter(w, rng), None
+        cur = torch.cuda.current_stream(w.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=w.device)
+        if self._wt_side is None or self._wt_side.shape != w.shape or self._wt_side.device != w.device:
+            self._wt_side = torch.empty_like(w)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            ops.neighbourhood_filter(w, rng, out=self._wt_side)
+        return self._wt_side, self._side
+
+    @staticmethod
+    def _join_filter(side):
+        if side is not None:
+            torch.cuda.current_stream(side.device).wait_stream(side)
 
     def _search(self, x, geom, w):
         """BMU search of the step.  Where the kernel can emit it, also the patch-major staging copy of the patch rows:

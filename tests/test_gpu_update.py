@@ -342,6 +342,30 @@ def test_cuda_graph_trainer_matches_eager_trainer():
                       what="weights after an eager step between graph replays")
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_filter_on_a_side_stream_gives_the_same_step(graph):
+    """W~ = T @ W runs on a side stream beside the search (SomTrainer(overlap_filter=True), fork / join by stream waits,
+    also inside a captured graph): same kernels on the same data, so losses and weights must be BIT-identical to the
+    one-stream order, step after step (a missing join would show up as a stale or half-written W~)."""
+    from oracle.step_oracle import synthetic_fmaps, trained_like_codebook
+    pd, k = (4, 4), 2048
+    w0 = trained_like_codebook(k, pd, 11)
+    trainers = []
+    for overlap in (True, False):
+        cb = somcb.Codebook(patch_dim=pd, image_dim=(32, 32), image_channel=4, num_embeddings=k,
+                            init_neighbour_range=k // 2)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(w0)
+        trainers.append(somcb.SomTrainer(cb.to(DEV), lr=1e-3, neighbourhood_step=4, use_cuda_graph=graph,
+                                         overlap_filter=overlap, small_step_kernel=False))
+    for step in range(12):
+        x = synthetic_fmaps(64, 500 + step).to(DEV)           # 4096 patches: the separate-kernel path
+        la, lb = trainers[0].step(x), trainers[1].step(x)
+        assert float(la) == float(lb), f"step {step}: loss {float(la)} vs {float(lb)}"
+        assert torch.equal(trainers[0].cb.codebook.weight.data, trainers[1].cb.codebook.weight.data), f"step {step}"
+    assert trainers[0]._side is not None and trainers[1]._side is None
+
+
 def test_trainer_nan_guard():
     """check_nan=True restores the reference's guard (train_codebook.py:237-238)."""
     from oracle.step_oracle import synthetic_fmaps, trained_like_codebook

@@ -38,6 +38,8 @@ def main():
     xs = [bench._fmaps(hi - lo, 5000 + 131 * b + rank, dev) for b in range(4)]
     cb = bench._codebook(16384, (4, 4), dev)
     tr = bench._make_trainer(cb, world, tail=tail, wt=wt)
+    if os.environ.get("TRACE_OVERLAP", "1") == "0":        # A/B: W~ filter in front of the search, on one stream
+        tr.overlap_filter = False
     if world > 1:
         tr.broadcast_weights(0)
     for i in range(10):
