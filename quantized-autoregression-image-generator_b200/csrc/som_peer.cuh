@@ -22,14 +22,27 @@ __device__ __forceinline__ float4 mm_ld_reduce(const float* mc) {
 // the squared error in fp64 -- the same bits on every rank.
 __device__ __forceinline__ float4 exact_tail(const Pads& bufs, int64_t q_tail, int world) {
     double sse = 0.0, cnt_hi = 0.0, cnt_lo = 0.0;
-    for (int r = 0; r < world; ++r) {
-        float4 t;
-        const float* p = reinterpret_cast<const float*>(bufs.p[r]) + 4 * q_tail;
-        asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p) : "memory");
-        sse += (double)t.x + (double)t.y;
-        cnt_hi += (double)t.z;
-        cnt_lo += (double)t.w;
+    // eight peer loads in flight, then the sums in rank order: issued one by one behind the fp64 adds that consume
+    // them, the loads were a chain of `world` NVLink round trips on the single thread every caller waits for
+    for (int r0 = 0; r0 < world; r0 += 8) {
+        float4 t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + u < world) {
+                const float* p = reinterpret_cast<const float*>(bufs.p[r0 + u]) + 4 * q_tail;
+                asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(t[u].x), "=f"(t[u].y), "=f"(t[u].z), "=f"(t[u].w) : "l"(p) : "memory");
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (r0 + u < world) {
+                sse += (double)t[u].x + (double)t[u].y;
+                cnt_hi += (double)t[u].z;
+                cnt_lo += (double)t[u].w;
+            }
+        }
     }
     const double cnt = cnt_hi * 4096.0 + cnt_lo;
     const float hi = (float)sse;
